@@ -1,0 +1,1013 @@
+// rcvd_api.cu -- host driver + C ABI (include/rcvd.h) of the B200 temporal-consistency solver.
+//
+// Replaces ceres::Solve as called from DepthVideoPoseOptimizer::poseOptimizationStep
+// (reference lib/PoseOptimizer.cpp:954-962) and ::normalizeDepth (:1117-1125): Levenberg-
+// Marquardt with Ceres' trust-region rules on the host, all arithmetic on the device.
+// There is NO CPU fallback: without a CUDA device rcvd_problem_create fails.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <limits>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "rcvd_eval.cuh"
+#include "rcvd_linalg.cuh"
+#include "rcvd_dense.cuh"
+
+using namespace rcvd;
+
+#define RCVD_API extern "C" __attribute__((visibility("default")))
+
+static thread_local std::string g_err = "";
+static int set_err(int code, const char* fmt, ...) {
+  char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+  g_err = buf; return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return set_err(RCVD_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+// ---- NCCL through dlopen (plumbing only; the data path collective is one all-reduce) ----
+namespace nccl {
+typedef struct { char internal[128]; } UniqueId;
+typedef void* Comm;
+static void* lib = nullptr;
+static int (*GetUniqueId)(UniqueId*) = nullptr;
+static int (*CommInitRank)(Comm*, int, UniqueId, int) = nullptr;
+static int (*AllReduce)(const void*, void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+static int (*CommDestroy)(Comm) = nullptr;
+static const char* (*GetErrorString)(int) = nullptr;
+static bool load() {
+  if (lib) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+  if (!lib) return false;
+  GetUniqueId = (int (*)(UniqueId*))dlsym(lib, "ncclGetUniqueId");
+  CommInitRank = (int (*)(Comm*, int, UniqueId, int))dlsym(lib, "ncclCommInitRank");
+  AllReduce = (int (*)(const void*, void*, size_t, int, int, Comm, cudaStream_t))dlsym(lib, "ncclAllReduce");
+  CommDestroy = (int (*)(Comm))dlsym(lib, "ncclCommDestroy");
+  GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+  return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
+}
+constexpr int kFloat64 = 8, kSum = 0;   // ncclFloat64, ncclSum
+}  // namespace nccl
+
+// ---- small vector kernels of the LM loop ----
+enum { SC_COST = 0, SC_CAND = 1, SC_GY = 2, SC_YHY = 3, SC_STEP2 = 4, SC_X2 = 5, SC_GMAX = 6, SC_GDOTD = 7, SC_DMAX = 8, SC_N = 16 };
+
+__global__ void k_extract_diag(const double* __restrict__ H, double* __restrict__ diag, int N, int npad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * npad) return;
+  const int f = i / npad, l = i % npad;
+  diag[i] = H[(size_t)f * npad * npad + (size_t)l * npad + l];
+}
+__global__ void k_jacobi_scale(const double* __restrict__ diag, double* __restrict__ S, int n, int enable) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) S[i] = enable ? 1.0 / (1.0 + sqrt(diag[i])) : 1.0;
+}
+// lmdiag = clamp(S^2 diagH) (unless reuse); D2 = lmdiag / radius; gs = S g
+__global__ void k_lm_prepare(const double* __restrict__ diagH, const double* __restrict__ S, const double* __restrict__ g, double* __restrict__ lmdiag,
+                             double* __restrict__ D2, double* __restrict__ gs, int n, int reuse, double radius, double dmin, double dmax) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double s = S[i];
+  double d = lmdiag[i];
+  if (!reuse) { d = fmin(fmax(s * s * diagH[i], dmin), dmax); lmdiag[i] = d; }
+  D2[i] = d / radius;
+  gs[i] = s * g[i];
+}
+__global__ void k_mul(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ o, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) o[i] = a[i] * b[i];
+}
+__device__ __forceinline__ double project_lb(const rcvd_config& c, const Layout& L, const uint8_t* in_range, int f, int l, double v) {
+  if (c.depth_lower_bound && l >= L.offD && l < L.offS && ((l - L.offD) % L.k) == 0 && in_range[f]) return fmax(v, 0.0);
+  return v;
+}
+// xc = Plus(x, alpha * (-y*S)) with bounds projection; accumulates |x - xc|^2 over active params,
+// g . delta and max|delta| (for the line search).  y, S, g have npad stride; x, xc nf stride.
+__global__ void __launch_bounds__(256) k_candidate(rcvd_config cfg, Layout L, const uint8_t* __restrict__ in_range, const uint8_t* __restrict__ active,
+                                                    const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ S,
+                                                    const double* __restrict__ g, double alpha, double* __restrict__ xc, double* __restrict__ scal, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double d2 = 0.0, gd = 0.0, dm = 0.0;
+  if (i < N * L.nf) {
+    const int f = i / L.nf, l = i % L.nf;
+    const size_t v = (size_t)f * L.npad + l;
+    const double delta = -y[v] * S[v];
+    const double xn = project_lb(cfg, L, in_range, f, l, x[i] + alpha * delta);
+    xc[i] = xn;
+    if (active[v]) { const double d = x[i] - xn; d2 = d * d; }
+    gd = g[v] * delta; dm = fabs(delta);
+  }
+  d2 = warp_sum(d2); gd = warp_sum(gd);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dm = fmax(dm, __shfl_xor_sync(0xffffffffu, dm, o));
+  if ((threadIdx.x & 31) == 0) {
+    red_add(scal + SC_STEP2, d2); red_add(scal + SC_GDOTD, gd);
+    atomicMax((unsigned long long*)(scal + SC_DMAX), (unsigned long long)__double_as_longlong(dm));   // dm >= 0: bit pattern is monotone
+  }
+}
+// |x|^2 over active params and max-norm of the projected gradient step x - Plus(x, -g)
+__global__ void __launch_bounds__(256) k_state_norms(rcvd_config cfg, Layout L, const uint8_t* __restrict__ in_range, const uint8_t* __restrict__ active,
+                                                      const double* __restrict__ x, const double* __restrict__ g, double* __restrict__ scal, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double x2 = 0.0, gm = 0.0;
+  if (i < N * L.nf) {
+    const int f = i / L.nf, l = i % L.nf;
+    const size_t v = (size_t)f * L.npad + l;
+    if (active[v]) {
+      x2 = x[i] * x[i];
+      gm = fabs(x[i] - project_lb(cfg, L, in_range, f, l, x[i] - g[v]));
+    }
+  }
+  x2 = warp_sum(x2);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) gm = fmax(gm, __shfl_xor_sync(0xffffffffu, gm, o));
+  if ((threadIdx.x & 31) == 0) {
+    red_add(scal + SC_X2, x2);
+    atomicMax((unsigned long long*)(scal + SC_GMAX), (unsigned long long)__double_as_longlong(gm));
+  }
+}
+__global__ void __launch_bounds__(256) k_dot2(const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ c,
+                                               const double* __restrict__ d, int n, double* __restrict__ scal, int s0, int s1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double p = 0.0, q = 0.0;
+  if (i < n) { p = a[i] * b[i]; q = c[i] * d[i]; }
+  p = warp_sum(p); q = warp_sum(q);
+  if ((threadIdx.x & 31) == 0) { red_add(scal + s0, p); red_add(scal + s1, q); }
+}
+__global__ void k_finalize_mask(rcvd_config cfg, Layout L, uint8_t* __restrict__ mask, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * L.npad) return;
+  const int l = i % L.npad;
+  if (l >= L.nf || is_const_local(cfg, L, l)) mask[i] = 0;
+}
+__global__ void k_project_state(rcvd_config cfg, Layout L, const uint8_t* __restrict__ in_range, double* __restrict__ x, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N * L.nf) x[i] = project_lb(cfg, L, in_range, i / L.nf, i % L.nf, x[i]);
+}
+__global__ void k_h_to_dense(const double* __restrict__ H, const HBlock* __restrict__ hb, int nblocks, double* __restrict__ out, int N, int nf, int npad) {
+  const int b = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nf * nf) return;
+  const int i = e / nf, j = e % nf;
+  const HBlock hbk = hb[b];
+  if (hbk.r == hbk.c && j > i) return;
+  const double v = H[(size_t)b * npad * npad + (size_t)i * npad + j];
+  const size_t U = (size_t)N * nf;
+  out[((size_t)hbk.r * nf + i) * U + (size_t)hbk.c * nf + j] = v;
+  out[((size_t)hbk.c * nf + j) * U + (size_t)hbk.r * nf + i] = v;
+}
+
+// ---------------------------------------------------------------------------
+struct Level { int frame_off, nframes; int trsm_off, ntrsm; int upd_off, nupd; int fwd_off, nfwd; };
+
+struct rcvd_problem {
+  rcvd_config cfg; Layout L; int N = 0; int device = 0;
+  cudaStream_t stream = nullptr;
+  // host inputs
+  std::vector<uint8_t> in_range; std::vector<double> median, adaptive;
+  std::vector<int32_t> pair_frames; std::vector<int64_t> offsets; std::vector<float> records_h;
+  std::vector<int32_t> struct_pairs;   // global frame-pair graph (multi-GPU); empty -> local pairs
+  int first_frame = 0, last_frame = -1;
+  // device problem data
+  float* d_records = nullptr; int32_t *d_tile_pair = nullptr, *d_tile_count = nullptr, *d_pair_frames = nullptr, *d_blk_of = nullptr;
+  int64_t* d_tile_begin = nullptr; uint8_t *d_in_range = nullptr, *d_active = nullptr;
+  double *d_median = nullptr, *d_adaptive = nullptr; float* d_scale_locs = nullptr; int nscale = 0;
+  int num_tiles = 0; int64_t C = 0;
+  // state & vectors
+  double *d_x = nullptr, *d_xc = nullptr, *d_xsave = nullptr;
+  double *d_g = nullptr, *d_S = nullptr, *d_diagH = nullptr, *d_lmdiag = nullptr, *d_D2 = nullptr, *d_gs = nullptr, *d_rhs = nullptr, *d_ytmp = nullptr,
+         *d_y = nullptr, *d_Sy = nullptr, *d_Hy = nullptr, *d_partial = nullptr, *d_scal = nullptr;
+  double* h_scal = nullptr;   // pinned
+  int npartial = 0;
+  // matrices
+  double *d_H = nullptr, *d_Lb = nullptr, *d_T = nullptr, *d_invL = nullptr, *d_invT = nullptr;
+  int nHblocks = 0, nLoff = 0; HBlock *d_hblocks = nullptr, *d_lblocks = nullptr; int* d_fail = nullptr;
+  std::vector<HBlock> hblocks;
+  // schedule
+  std::vector<Level> levels; int *d_lvl_frames = nullptr; GemmTask *d_trsm_tasks = nullptr, *d_upd_tasks = nullptr; int2 *d_trsm_pairs = nullptr, *d_upd_pairs = nullptr;
+  SolveTask *d_fwd_tasks = nullptr, *d_col_tasks = nullptr; int* d_col_ptr = nullptr;
+  cudaGraphExec_t solve_graph = nullptr;
+  bool structure_ready = false, constraints_set = false, frames_set = false;
+  // multi GPU
+  int nranks = 1, rank = 0; nccl::Comm comm = nullptr;
+  int64_t launches = 0, graph_launches = 0;
+  std::vector<double> h_state; bool state_dirty = false;
+  double *d_g2 = nullptr, *d_delta = nullptr; int* h_fail = nullptr;
+  cudaEvent_t ev[8] = {nullptr};
+  std::vector<void*> allocs;
+  rcvd_problem() {}
+};
+
+template <class T> static int dalloc(rcvd_problem* p, T** ptr, size_t count) {
+  *ptr = nullptr;
+  if (count == 0) count = 1;
+  cudaError_t e = cudaMalloc((void**)ptr, count * sizeof(T));
+  if (e != cudaSuccess) return set_err(RCVD_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+  p->allocs.push_back(*ptr);
+  return RCVD_OK;
+}
+template <class T> static int upload(rcvd_problem* p, T** ptr, const std::vector<T>& v) {
+  int rc = dalloc(p, ptr, v.size()); if (rc) return rc;
+  if (!v.empty()) CK(cudaMemcpyAsync(*ptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, p->stream));
+  return RCVD_OK;
+}
+static void free_all(rcvd_problem* p) {
+  if (p->solve_graph) { cudaGraphExecDestroy(p->solve_graph); p->solve_graph = nullptr; }
+  for (void* q : p->allocs) cudaFree(q);
+  p->allocs.clear();
+  if (p->h_scal) { cudaFreeHost(p->h_scal); p->h_scal = nullptr; }
+  p->structure_ready = false;
+}
+
+static DevProblem dev_problem(const rcvd_problem* p) {
+  DevProblem d; d.cfg = p->cfg; d.L = p->L; d.N = p->N; d.num_tiles = p->num_tiles; d.num_constraints = p->C;
+  d.records = p->d_records; d.tile_pair = p->d_tile_pair; d.tile_begin = p->d_tile_begin; d.tile_count = p->d_tile_count;
+  d.pair_frames = p->d_pair_frames; d.blk_of = p->d_blk_of; d.in_range = p->d_in_range; d.median = p->d_median;
+  d.adaptive = p->adaptive.empty() ? nullptr : p->d_adaptive; d.scale_locs = p->d_scale_locs; d.num_scale_locs = p->nscale;
+  d.rank = p->rank; d.nranks = p->nranks;
+  return d;
+}
+
+// ---- structure: block layout, elimination order, level schedule ----
+static int build_structure(rcvd_problem* p) {
+  free_all(p);
+  const int N = p->N; const Layout& L = p->L; const int npad = L.npad; const size_t bs = (size_t)npad * npad;
+  CK(cudaSetDevice(p->device));
+  // frame graph
+  std::vector<std::set<int>> adj(N);
+  auto addEdge = [&](int a, int b) { if (a != b) { adj[a].insert(b); adj[b].insert(a); } };
+  const std::vector<int32_t>& sp = p->struct_pairs.empty() ? p->pair_frames : p->struct_pairs;
+  for (size_t i = 0; i + 1 < sp.size(); i += 2) {
+    const int a = sp[i], b = sp[i + 1];
+    if (a < 0 || a >= N || b < 0 || b >= N) return set_err(RCVD_ERR_INVALID, "pair frame index out of range");
+    addEdge(a, b);
+    if (p->cfg.intr_opt == RCVD_INTR_SHARED) { addEdge(a, 0); addEdge(b, 0); }
+  }
+  if (p->cfg.position_reg > 0.0) for (int f = 0; f + 2 < N; ++f) { addEdge(f, f + 1); addEdge(f, f + 2); addEdge(f + 1, f + 2); }
+  std::vector<std::set<int>> orig = adj;
+  // greedy minimum-degree elimination (ties -> lowest frame id)
+  std::vector<int> order, pos(N, -1); std::vector<std::vector<int>> cs(N);
+  {
+    std::vector<uint8_t> done(N, 0);
+    for (int it = 0; it < N; ++it) {
+      int best = -1; size_t bd = (size_t)-1;
+      for (int f = 0; f < N; ++f) if (!done[f] && adj[f].size() < bd) { bd = adj[f].size(); best = f; }
+      done[best] = 1; pos[best] = it; order.push_back(best);
+      std::vector<int> nb(adj[best].begin(), adj[best].end());
+      cs[best] = nb;
+      for (int a : nb) adj[a].erase(best);
+      for (size_t i = 0; i < nb.size(); ++i) for (size_t j = i + 1; j < nb.size(); ++j) { adj[nb[i]].insert(nb[j]); adj[nb[j]].insert(nb[i]); }
+    }
+    for (int f = 0; f < N; ++f) std::sort(cs[f].begin(), cs[f].end(), [&](int a, int b) { return pos[a] < pos[b]; });
+  }
+  // L off-diagonal blocks (r later than c)
+  std::map<std::pair<int, int>, int> lid; int nLoff = 0;
+  for (int k : order) for (int r : cs[k]) lid[{r, k}] = N + nLoff++;
+  p->nLoff = nLoff;
+  // H blocks: diagonal first, then original off-diagonals oriented (later, earlier)
+  p->hblocks.clear();
+  std::vector<int32_t> blk_of((size_t)N * N, -1);
+  for (int f = 0; f < N; ++f) p->hblocks.push_back({f, f, f});
+  for (int a = 0; a < N; ++a) for (int b : orig[a]) if (a < b) {
+    const int r = pos[a] > pos[b] ? a : b, c = pos[a] > pos[b] ? b : a;
+    const int hid = (int)p->hblocks.size();
+    p->hblocks.push_back({lid[{r, c}], r, c});
+    blk_of[(size_t)r * N + c] = hid * 2 + 1;   // (fa = r) is the row side
+    blk_of[(size_t)c * N + r] = hid * 2 + 0;
+  }
+  p->nHblocks = (int)p->hblocks.size();
+  // all L blocks with their H source (or -1)
+  std::vector<HBlock> lblocks(N + nLoff);
+  for (int f = 0; f < N; ++f) lblocks[f] = {f, f, f};
+  for (auto& kv : lid) lblocks[kv.second] = {-1, kv.first.first, kv.first.second};
+  for (int h = N; h < p->nHblocks; ++h) lblocks[p->hblocks[h].lblk].lblk = h;
+  // levels
+  std::vector<int> lvl(N, 0); int nl = 0;
+  for (int k : order) { for (int a : cs[k]) lvl[a] = std::max(lvl[a], lvl[k] + 1); nl = std::max(nl, lvl[k] + 1); }
+  std::vector<std::vector<int>> lf(nl);
+  for (int k : order) lf[lvl[k]].push_back(k);
+  std::vector<int> lvl_frames; std::vector<GemmTask> trsm_tasks, upd_tasks; std::vector<int2> trsm_pairs, upd_pairs;
+  std::vector<SolveTask> fwd_tasks, col_tasks; std::vector<int> col_ptr(N + 1, 0);
+  p->levels.clear();
+  for (int l = 0; l < nl; ++l) {
+    Level lv; lv.frame_off = (int)lvl_frames.size(); lv.nframes = (int)lf[l].size();
+    lv.trsm_off = (int)trsm_tasks.size(); lv.upd_off = (int)upd_tasks.size(); lv.fwd_off = (int)fwd_tasks.size();
+    std::map<int, std::vector<int2>> upd;   // target L block id -> source pairs
+    for (int k : lf[l]) {
+      lvl_frames.push_back(k);
+      for (int r : cs[k]) {
+        const int id = lid[{r, k}];
+        trsm_tasks.push_back({id - N, (int)trsm_pairs.size(), 1, 0});
+        trsm_pairs.push_back(make_int2(id, k));
+        fwd_tasks.push_back({id - N, r, k});
+      }
+      for (size_t a = 0; a < cs[k].size(); ++a) for (size_t b = 0; b <= a; ++b) {
+        const int r = cs[k][a], c = cs[k][b];
+        const int target = (r == c) ? r : lid[{r, c}];
+        upd[target].push_back(make_int2(lid[{r, k}] - N, lid[{c, k}] - N));
+      }
+    }
+    for (auto& kv : upd) {
+      upd_tasks.push_back({kv.first, (int)upd_pairs.size(), (int)kv.second.size(), kv.first < N ? 1 : 0});
+      upd_pairs.insert(upd_pairs.end(), kv.second.begin(), kv.second.end());
+    }
+    lv.ntrsm = (int)trsm_tasks.size() - lv.trsm_off; lv.nupd = (int)upd_tasks.size() - lv.upd_off; lv.nfwd = (int)fwd_tasks.size() - lv.fwd_off;
+    p->levels.push_back(lv);
+  }
+  for (int k = 0; k < N; ++k) { col_ptr[k] = (int)col_tasks.size(); for (int r : cs[k]) col_tasks.push_back({lid[{r, k}] - N, r, k}); }
+  col_ptr[N] = (int)col_tasks.size();
+
+  // ---- device allocations ----
+  int rc;
+#define UP(ptr, vec) if ((rc = upload(p, &(ptr), vec))) return rc
+  UP(p->d_blk_of, blk_of); UP(p->d_hblocks, p->hblocks); UP(p->d_lblocks, lblocks); UP(p->d_lvl_frames, lvl_frames);
+  UP(p->d_trsm_tasks, trsm_tasks); UP(p->d_upd_tasks, upd_tasks); UP(p->d_trsm_pairs, trsm_pairs); UP(p->d_upd_pairs, upd_pairs);
+  UP(p->d_fwd_tasks, fwd_tasks); UP(p->d_col_tasks, col_tasks); UP(p->d_col_ptr, col_ptr);
+  // tiles
+  const int np = (int)(p->pair_frames.size() / 2);
+  std::vector<int32_t> tile_pair, tile_count; std::vector<int64_t> tile_begin;
+  for (int i = 0; i < np; ++i)
+    for (int64_t b = p->offsets[i]; b < p->offsets[i + 1]; b += kTile) { tile_pair.push_back(i); tile_begin.push_back(b); tile_count.push_back((int32_t)std::min<int64_t>(kTile, p->offsets[i + 1] - b)); }
+  p->num_tiles = (int)tile_pair.size(); p->C = p->offsets.empty() ? 0 : p->offsets.back();
+  UP(p->d_tile_pair, tile_pair); UP(p->d_tile_begin, tile_begin); UP(p->d_tile_count, tile_count);
+  UP(p->d_pair_frames, p->pair_frames); UP(p->d_records, p->records_h);
+  UP(p->d_in_range, p->in_range); UP(p->d_median, p->median);
+  if (!p->adaptive.empty()) UP(p->d_adaptive, p->adaptive);
+  {
+    // scale-regulariser lattice in float32, lib/PoseOptimizer.cpp:1382-1385
+    std::vector<float> locs; const int gx = p->cfg.scale_grid_x, gy = p->cfg.scale_grid_y;
+    for (int y = 0; y < gy; ++y) for (int x = 0; x < gx; ++x) {
+      // host code is built without -mfma, so these float ops are not contracted
+      const float fx = -1.f + 2.f * x / (gx - 1);
+      const float fy = -1.f + 2.f * y / (gy - 1);
+      locs.push_back(fx); locs.push_back(fy);
+    }
+    p->nscale = (int)(locs.size() / 2);
+    UP(p->d_scale_locs, locs);
+  }
+#undef UP
+  p->first_frame = 0; p->last_frame = -1;
+  { bool any = false; for (int f = 0; f < N; ++f) if (p->in_range[f]) { if (!any) { p->first_frame = f; any = true; } p->last_frame = f; } }
+  const size_t Upad = (size_t)N * npad, U = (size_t)N * L.nf;
+#define DA(ptr, n) if ((rc = dalloc(p, &(ptr), (n)))) return rc
+  DA(p->d_x, U); DA(p->d_xc, U); DA(p->d_xsave, U);
+  DA(p->d_g, Upad + 8); DA(p->d_S, Upad); DA(p->d_diagH, Upad); DA(p->d_lmdiag, Upad); DA(p->d_D2, Upad); DA(p->d_gs, Upad); DA(p->d_rhs, Upad);
+  DA(p->d_g2, Upad + 8); DA(p->d_delta, Upad);
+  DA(p->d_ytmp, Upad); DA(p->d_y, Upad); DA(p->d_Sy, Upad); DA(p->d_Hy, Upad); DA(p->d_scal, SC_N); DA(p->d_active, Upad); DA(p->d_fail, 1);
+  const RegCounts rcn = reg_counts(p->cfg, L, N, p->nscale);
+  p->npartial = p->num_tiles + (rcn.total + 127) / 128 + 1;
+  DA(p->d_partial, (size_t)p->npartial);
+  DA(p->d_H, (size_t)p->nHblocks * bs); DA(p->d_Lb, (size_t)(N + nLoff) * bs); DA(p->d_T, (size_t)std::max(nLoff, 1) * bs);
+  DA(p->d_invL, (size_t)N * bs); DA(p->d_invT, (size_t)N * npad * 16);
+#undef DA
+  CK(cudaMallocHost((void**)&p->h_scal, (SC_N + 2) * sizeof(double)));
+  p->h_fail = (int*)(p->h_scal + SC_N);
+  CK(cudaMemsetAsync(p->d_x, 0, U * sizeof(double), p->stream));
+  CK(cudaMemsetAsync(p->d_lmdiag, 0, Upad * sizeof(double), p->stream));
+  CK(cudaMemsetAsync(p->d_S, 0, Upad * sizeof(double), p->stream));
+  // active mask
+  CK(cudaMemsetAsync(p->d_active, 0, Upad, p->stream));
+  DevProblem d = dev_problem(p);
+  if (p->num_tiles > 0) k_mark_static<<<p->num_tiles, kTile, 0, p->stream>>>(d, p->d_active);
+  if (rcn.total > 0) {
+    DevProblem d1 = d; d1.nranks = 1; d1.rank = 0;   // mark regardless of rank ownership
+    k_regularisers<2><<<(rcn.total + 127) / 128, 128, 0, p->stream>>>(d1, rcn, p->d_x, nullptr, nullptr, nullptr, p->d_active, p->first_frame, p->last_frame);
+  }
+  k_finalize_mask<<<(int)((Upad + 255) / 256), 256, 0, p->stream>>>(p->cfg, L, p->d_active, N);
+  CK(cudaGetLastError());
+  // kernels that need > 48 KB dynamic smem
+  const int dyn = npad * 17 * (int)sizeof(double);
+  if (dyn > 200 * 1024) return set_err(RCVD_ERR_INVALID, "frame block too large for the single-CTA factor kernel (npad=%d)", npad);
+  CK(cudaFuncSetAttribute(k_potrf, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+  CK(cudaFuncSetAttribute(k_trinv, cudaFuncAttributeMaxDynamicSharedMemorySize, npad * 16 * (int)sizeof(double)));
+  CK(cudaStreamSynchronize(p->stream));
+  p->structure_ready = true;
+  return RCVD_OK;
+}
+
+// Enqueues factorisation of (S H S + D2) and the solve y = A^{-1} gs on p->stream.
+static int enqueue_factor_solve(rcvd_problem* p) {
+  const Layout& L = p->L; const int N = p->N, npad = L.npad; cudaStream_t st = p->stream;
+  const int nL = N + p->nLoff;
+  const int tiles = (npad + 63) / 64;
+  k_load_factor<<<dim3((npad * npad + 255) / 256, nL), 256, 0, st>>>(p->d_H, p->d_Lb, p->d_lblocks, p->d_S, p->d_D2, npad, L.nf);
+  p->launches += 1;
+  for (const Level& lv : p->levels) {
+    k_potrf<<<lv.nframes, kPotrfThreads, npad * 17 * sizeof(double), st>>>(p->d_Lb, p->d_invT, p->d_lvl_frames + lv.frame_off, npad, p->d_fail);
+    k_trinv<<<dim3(npad / 16, lv.nframes), 256, npad * 16 * sizeof(double), st>>>(p->d_Lb, p->d_invT, p->d_invL, p->d_lvl_frames + lv.frame_off, npad);
+    p->launches += 2;
+    if (lv.ntrsm > 0) { k_gemm_nt<<<dim3(tiles, tiles, lv.ntrsm), 128, 0, st>>>(p->d_T, p->d_Lb, p->d_invL, p->d_trsm_tasks + lv.trsm_off, p->d_trsm_pairs, npad, 1.0, 0.0); p->launches++; }
+    if (lv.nupd > 0) { k_gemm_nt<<<dim3(tiles, tiles, lv.nupd), 128, 0, st>>>(p->d_Lb, p->d_T, p->d_T, p->d_upd_tasks + lv.upd_off, p->d_upd_pairs, npad, -1.0, 1.0); p->launches++; }
+  }
+  CK(cudaMemcpyAsync(p->d_rhs, p->d_gs, (size_t)N * npad * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  for (const Level& lv : p->levels) {
+    k_fwd_diag<<<dim3((npad + 7) / 8, lv.nframes), 256, 0, st>>>(p->d_invL, p->d_rhs, p->d_ytmp, p->d_lvl_frames + lv.frame_off, npad);
+    p->launches++;
+    if (lv.nfwd > 0) { k_fwd_update<<<dim3((npad + 7) / 8, lv.nfwd), 256, 0, st>>>(p->d_T, p->d_ytmp, p->d_rhs, p->d_fwd_tasks + lv.fwd_off, npad); p->launches++; }
+  }
+  for (int l = (int)p->levels.size() - 1; l >= 0; --l) {
+    const Level& lv = p->levels[l];
+    k_bwd_update<<<dim3((npad + 255) / 256, lv.nframes), 256, 0, st>>>(p->d_T, p->d_y, p->d_ytmp, p->d_lvl_frames + lv.frame_off, p->d_col_ptr, p->d_col_tasks, npad);
+    k_bwd_diag<<<dim3((npad + 255) / 256, lv.nframes), 256, 0, st>>>(p->d_invL, p->d_ytmp, p->d_y, p->d_lvl_frames + lv.frame_off, npad);
+    p->launches += 2;
+  }
+  CK(cudaGetLastError());
+  return RCVD_OK;
+}
+
+// factor+solve through a CUDA graph (the level schedule is ~5 launches per level)
+static int factor_solve(rcvd_problem* p) {
+  if (!p->solve_graph) {
+    cudaGraph_t graph;
+    const int64_t l0 = p->launches;
+    CK(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_factor_solve(p);
+    cudaError_t e = cudaStreamEndCapture(p->stream, &graph);
+    if (rc) return rc;
+    if (e != cudaSuccess) return set_err(RCVD_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    CK(cudaGraphInstantiate(&p->solve_graph, graph, 0));
+    cudaGraphDestroy(graph);
+    p->graph_launches = p->launches - l0;
+    p->launches = l0;
+  }
+  CK(cudaGraphLaunch(p->solve_graph, p->stream));
+  p->launches += p->graph_launches;
+  return RCVD_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Evaluation
+// ---------------------------------------------------------------------------
+static int allreduce(rcvd_problem* p, double* buf, size_t count) {
+  if (p->nranks <= 1) return RCVD_OK;
+  const int r = nccl::AllReduce(buf, buf, count, nccl::kFloat64, nccl::kSum, p->comm, p->stream);
+  if (r != 0) return set_err(RCVD_ERR_NCCL, "ncclAllReduce failed: %s", nccl::GetErrorString ? nccl::GetErrorString(r) : "?");
+  return RCVD_OK;
+}
+
+// Cost (-> d_scal[slot]) at state x; optionally gradient (gout, npad stride) and H.
+static int enqueue_evaluate(rcvd_problem* p, const double* x, bool wantG, bool wantH, double* gout, int slot) {
+  const Layout& L = p->L; const int N = p->N, npad = L.npad; cudaStream_t st = p->stream;
+  const size_t bs = (size_t)npad * npad, Upad = (size_t)N * npad;
+  DevProblem d = dev_problem(p);
+  const RegCounts rcn = reg_counts(p->cfg, L, N, p->nscale);
+  const int regblocks = (rcn.total + 127) / 128;
+  if (wantH) CK(cudaMemsetAsync(p->d_H, 0, (size_t)p->nHblocks * bs * sizeof(double), st));
+  if (wantG) CK(cudaMemsetAsync(gout, 0, (Upad + 8) * sizeof(double), st));
+  if (p->num_tiles > 0) {
+    if (wantH) k_accumulate_generic<true><<<p->num_tiles, kTile, 0, st>>>(d, x, p->d_H, gout, p->d_partial);
+    else if (wantG) k_accumulate_generic<false><<<p->num_tiles, kTile, 0, st>>>(d, x, nullptr, gout, p->d_partial);
+    else k_cost_static<<<p->num_tiles, kTile, 0, st>>>(d, x, p->d_partial);
+    p->launches++;
+  }
+  if (regblocks > 0) {
+    double* part = p->d_partial + p->num_tiles;
+    if (wantH) k_regularisers<1><<<regblocks, 128, 0, st>>>(d, rcn, x, p->d_H, gout, part, nullptr, p->first_frame, p->last_frame);
+    else if (wantG) k_regularisers<3><<<regblocks, 128, 0, st>>>(d, rcn, x, nullptr, gout, part, nullptr, p->first_frame, p->last_frame);
+    else k_regularisers<0><<<regblocks, 128, 0, st>>>(d, rcn, x, nullptr, nullptr, part, nullptr, p->first_frame, p->last_frame);
+    p->launches++;
+  }
+  k_reduce_partials<<<1, 1024, 0, st>>>(p->d_partial, p->num_tiles + regblocks, p->d_scal, slot);
+  p->launches++;
+  CK(cudaGetLastError());
+  if (p->nranks > 1) {
+    int rc;
+    if (wantH && (rc = allreduce(p, p->d_H, (size_t)p->nHblocks * bs))) return rc;
+    if (wantG && (rc = allreduce(p, gout, Upad))) return rc;
+    if ((rc = allreduce(p, p->d_scal + slot, 1))) return rc;
+  }
+  return RCVD_OK;
+}
+
+static int ensure_ready(rcvd_problem* p) {
+  if (!p->structure_ready) {
+    if (p->offsets.empty()) { p->offsets.assign(1, 0); }
+    if (p->in_range.empty()) p->in_range.assign(p->N, 1);
+    if (p->median.empty()) p->median.assign(p->N, 1.0);
+    int rc = build_structure(p); if (rc) return rc;
+    p->state_dirty = true;
+  }
+  if (p->state_dirty) {
+    if (p->h_state.size() != (size_t)p->N * p->L.nf) p->h_state.assign((size_t)p->N * p->L.nf, 0.0);
+    CK(cudaMemcpyAsync(p->d_x, p->h_state.data(), p->h_state.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    p->state_dirty = false;
+  }
+  return RCVD_OK;
+}
+
+static int read_scalars(rcvd_problem* p) {
+  CK(cudaMemcpyAsync(p->h_scal, p->d_scal, SC_N * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaMemcpyAsync(p->h_fail, p->d_fail, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  return RCVD_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Polynomial minimisation for the Armijo line search (ceres/polynomial.cc semantics)
+// ---------------------------------------------------------------------------
+namespace ls {
+struct Sample { double x, value, gradient; bool valueValid, gradValid; };
+static double evalPoly(const std::vector<double>& p, double x) { double v = 0; for (double c : p) v = v * x + c; return v; }
+static bool solveDense(std::vector<std::vector<double>> A, std::vector<double> b, std::vector<double>& x) {
+  const int n = (int)b.size(); std::vector<int> perm(n); for (int i = 0; i < n; ++i) perm[i] = i;
+  for (int k = 0; k < n; ++k) {
+    int pr = k, pc = k; double best = 0;
+    for (int i = k; i < n; ++i) for (int j = k; j < n; ++j) if (std::fabs(A[i][j]) > best) { best = std::fabs(A[i][j]); pr = i; pc = j; }
+    if (best == 0) return false;
+    std::swap(A[k], A[pr]); std::swap(b[k], b[pr]);
+    for (int i = 0; i < n; ++i) std::swap(A[i][k], A[i][pc]);
+    std::swap(perm[k], perm[pc]);
+    for (int i = k + 1; i < n; ++i) { const double f = A[i][k] / A[k][k]; for (int j = k; j < n; ++j) A[i][j] -= f * A[k][j]; b[i] -= f * b[k]; }
+  }
+  std::vector<double> y(n);
+  for (int i = n - 1; i >= 0; --i) { double s = b[i]; for (int j = i + 1; j < n; ++j) s -= A[i][j] * y[j]; y[i] = s / A[i][i]; }
+  x.assign(n, 0.0); for (int i = 0; i < n; ++i) x[perm[i]] = y[i];
+  return true;
+}
+static std::vector<double> realRoots(std::vector<double> p) {
+  while (!p.empty() && p[0] == 0.0) p.erase(p.begin());
+  std::vector<double> out; const int d = (int)p.size() - 1; if (d < 1) return out;
+  if (d == 1) { out.push_back(-p[1] / p[0]); return out; }
+  if (d == 2) { const double a = p[0], b = p[1], c = p[2], D = b * b - 4 * a * c; if (D >= 0) { const double sq = std::sqrt(D); out.push_back((-b + sq) / (2 * a)); out.push_back((-b - sq) / (2 * a)); } else { out.push_back(-b / (2 * a)); out.push_back(-b / (2 * a)); } return out; }
+  std::vector<std::pair<double, double>> z(d);
+  for (int i = 0; i < d; ++i) { const double ang = 2 * M_PI * i / d + 0.4; z[i] = {0.9 * std::cos(ang), 0.9 * std::sin(ang)}; }
+  auto cmul = [](std::pair<double, double> a, std::pair<double, double> b) { return std::make_pair(a.first * b.first - a.second * b.second, a.first * b.second + a.second * b.first); };
+  auto cdiv = [](std::pair<double, double> a, std::pair<double, double> b) { const double dd = b.first * b.first + b.second * b.second; return std::make_pair((a.first * b.first + a.second * b.second) / dd, (a.second * b.first - a.first * b.second) / dd); };
+  for (int it = 0; it < 500; ++it) {
+    double mx = 0;
+    for (int i = 0; i < d; ++i) {
+      std::pair<double, double> v = {p[0], 0.0};
+      for (int j = 1; j <= d; ++j) { v = cmul(v, z[i]); v.first += p[j]; }
+      std::pair<double, double> den = {p[0], 0.0};
+      for (int j = 0; j < d; ++j) if (j != i) den = cmul(den, {z[i].first - z[j].first, z[i].second - z[j].second});
+      auto dl = cdiv(v, den); z[i].first -= dl.first; z[i].second -= dl.second;
+      mx = std::max(mx, std::fabs(dl.first) + std::fabs(dl.second));
+    }
+    if (mx < 1e-14) break;
+  }
+  for (auto& r : z) out.push_back(r.first);
+  return out;
+}
+static double minimizeInterpolating(const std::vector<Sample>& s, double xmin, double xmax) {
+  int nc = 0; for (auto& q : s) { if (q.valueValid) ++nc; if (q.gradValid) ++nc; }
+  const int deg = nc - 1;
+  std::vector<std::vector<double>> A; std::vector<double> b;
+  for (auto& q : s) {
+    if (q.valueValid) { std::vector<double> row(nc); for (int j = 0; j <= deg; ++j) row[j] = std::pow(q.x, deg - j); A.push_back(row); b.push_back(q.value); }
+    if (q.gradValid) { std::vector<double> row(nc); for (int j = 0; j < deg; ++j) row[j] = (deg - j) * std::pow(q.x, deg - j - 1); row[deg] = 0; A.push_back(row); b.push_back(q.gradient); }
+  }
+  std::vector<double> poly; if (!solveDense(A, b, poly)) return 0.5 * (xmin + xmax);
+  double ox = (xmin + xmax) / 2.0, ov = evalPoly(poly, ox);
+  const double vmin = evalPoly(poly, xmin); if (vmin < ov) { ov = vmin; ox = xmin; }
+  const double vmax = evalPoly(poly, xmax); if (vmax < ov) { ov = vmax; ox = xmax; }
+  if (poly.size() <= 2) return ox;
+  std::vector<double> der;
+  for (int j = 0; j < deg; ++j) der.push_back((deg - j) * poly[j]);
+  for (double r : realRoots(der)) { if (r < xmin || r > xmax) continue; const double v = evalPoly(poly, r); if (v < ov) { ov = v; ox = r; } }
+  return ox;
+}
+}  // namespace ls
+
+__global__ void k_make_delta(const double* __restrict__ y, const double* __restrict__ S, double* __restrict__ delta, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) delta[i] = -y[i] * S[i];
+}
+
+static inline int nblk(size_t n, int b = 256) { return (int)((n + b - 1) / b); }
+
+// model = gs.y - 1/2 (Sy)^T H (Sy); leaves GY, YHY in d_scal
+static int enqueue_model_terms(rcvd_problem* p) {
+  const int N = p->N, npad = p->L.npad; const size_t Upad = (size_t)N * npad; cudaStream_t st = p->stream;
+  k_mul<<<nblk(Upad), 256, 0, st>>>(p->d_S, p->d_y, p->d_Sy, (int)Upad);
+  CK(cudaMemsetAsync(p->d_Hy, 0, Upad * sizeof(double), st));
+  k_spmv_sym<<<dim3((npad + 7) / 8, p->nHblocks), 256, 0, st>>>(p->d_H, p->d_hblocks, p->d_Sy, p->d_Hy, npad);
+  k_dot2<<<nblk(Upad), 256, 0, st>>>(p->d_gs, p->d_y, p->d_Sy, p->d_Hy, (int)Upad, p->d_scal, SC_GY, SC_YHY);
+  k_make_delta<<<nblk(Upad), 256, 0, st>>>(p->d_y, p->d_S, p->d_delta, (int)Upad);
+  p->launches += 4;
+  return RCVD_OK;
+}
+
+__global__ void __launch_bounds__(256) k_candidate2(rcvd_config cfg, Layout L, const uint8_t* __restrict__ in_range, const uint8_t* __restrict__ active,
+                                                     const double* __restrict__ x, const double* __restrict__ delta, const double* __restrict__ g,
+                                                     double alpha, double* __restrict__ xc, double* __restrict__ scal, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double d2 = 0.0, gd = 0.0, dm = 0.0;
+  if (i < N * L.nf) {
+    const int f = i / L.nf, l = i % L.nf;
+    const size_t v = (size_t)f * L.npad + l;
+    const double dl = delta[v];
+    const double xn = project_lb(cfg, L, in_range, f, l, x[i] + alpha * dl);
+    xc[i] = xn;
+    if (active[v]) { const double d = x[i] - xn; d2 = d * d; }
+    gd = g[v] * dl; dm = fabs(dl);
+  }
+  d2 = warp_sum(d2); gd = warp_sum(gd);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dm = fmax(dm, __shfl_xor_sync(0xffffffffu, dm, o));
+  if ((threadIdx.x & 31) == 0) {
+    red_add(scal + SC_STEP2, d2); red_add(scal + SC_GDOTD, gd);
+    atomicMax((unsigned long long*)(scal + SC_DMAX), (unsigned long long)__double_as_longlong(dm));
+  }
+}
+
+static int enqueue_candidate(rcvd_problem* p, double alpha, const double* g) {
+  const size_t U = (size_t)p->N * p->L.nf;
+  k_candidate2<<<nblk(U), 256, 0, p->stream>>>(p->cfg, p->L, p->d_in_range, p->d_active, p->d_x, p->d_delta, g, alpha, p->d_xc, p->d_scal, p->N);
+  p->launches++;
+  return RCVD_OK;
+}
+
+static float ev_ms(cudaEvent_t a, cudaEvent_t b) { float m = 0; cudaEventElapsedTime(&m, a, b); return m; }
+
+// ---------------------------------------------------------------------------
+// Levenberg-Marquardt, Ceres semantics (TrustRegionMinimizer::Minimize restated).
+// ---------------------------------------------------------------------------
+static int lm_solve(rcvd_problem* p, const rcvd_solve_options& o, rcvd_solve_summary& sum) {
+  using clk = std::chrono::steady_clock;
+  const auto t0 = clk::now();
+  memset(&sum, 0, sizeof(sum));
+  int rc = ensure_ready(p); if (rc) return rc;
+  const Layout& L = p->L; const int N = p->N, npad = L.npad; const size_t Upad = (size_t)N * npad, U = (size_t)N * L.nf; cudaStream_t st = p->stream;
+  const int64_t launches0 = p->launches;
+  sum.num_constraints = p->C;
+  const bool constrained = p->cfg.depth_lower_bound && L.nd > 0;
+  for (int i = 0; i < 8; ++i) if (!p->ev[i]) CK(cudaEventCreate(&p->ev[i]));
+  if (constrained) { k_project_state<<<nblk(U), 256, 0, st>>>(p->cfg, L, p->d_in_range, p->d_x, N); p->launches++; }
+  // user-visible minimum-cost iterate
+  CK(cudaMemcpyAsync(p->d_xsave, p->d_x, U * sizeof(double), cudaMemcpyDeviceToDevice, st));
+
+  auto full_eval = [&]() -> int {   // cost, gradient, H, diag, norms at d_x
+    CK(cudaMemsetAsync(p->d_scal, 0, SC_N * sizeof(double), st));
+    CK(cudaEventRecord(p->ev[0], st));
+    int r = enqueue_evaluate(p, p->d_x, true, true, p->d_g, SC_COST); if (r) return r;
+    CK(cudaEventRecord(p->ev[1], st));
+    k_extract_diag<<<nblk(Upad), 256, 0, st>>>(p->d_H, p->d_diagH, N, npad);
+    k_state_norms<<<nblk(U), 256, 0, st>>>(p->cfg, L, p->d_in_range, p->d_active, p->d_x, p->d_g, p->d_scal, N);
+    p->launches += 2;
+    r = read_scalars(p); if (r) return r;
+    sum.eval_ms += ev_ms(p->ev[0], p->ev[1]);
+    return RCVD_OK;
+  };
+  if ((rc = full_eval())) return rc;
+  double xCost = p->h_scal[SC_COST], xNorm = std::sqrt(p->h_scal[SC_X2]), gmax = p->h_scal[SC_GMAX];
+  sum.initial_cost = xCost;
+  k_jacobi_scale<<<nblk(Upad), 256, 0, st>>>(p->d_diagH, p->d_S, (int)Upad, o.jacobi_scaling);
+  p->launches++;
+  double radius = o.initial_radius, decrease = 2.0; bool reuseDiag = false;
+  double minimumCost = xCost;
+  int iter = 0, invalid = 0; bool stepSuccessful = true;
+  auto finish = [&](int term, const char* msg) { sum.termination = term; snprintf(sum.message, sizeof(sum.message), "%s", msg); };
+  finish(RCVD_TERM_NO_CONVERGENCE, "");
+  if (o.verbose) fprintf(stderr, "[rcvd] iter      cost      cost_change  |gradient|   |step|    tr_ratio  tr_radius\n[rcvd] %4d %.6e %10.2e %10.2e %10.2e %10.2e %10.2e\n", 0, xCost, 0.0, gmax, 0.0, 0.0, radius);
+  for (;;) {
+    if (stepSuccessful) {
+      ++sum.num_successful_steps;
+      if (xCost < minimumCost || iter == 0) { minimumCost = xCost; CK(cudaMemcpyAsync(p->d_xsave, p->d_x, U * sizeof(double), cudaMemcpyDeviceToDevice, st)); }
+    } else ++sum.num_unsuccessful_steps;
+    if (iter >= o.max_iterations) { finish(RCVD_TERM_NO_CONVERGENCE, "Maximum number of iterations reached."); break; }
+    if (stepSuccessful && gmax <= o.gradient_tolerance) { finish(RCVD_TERM_CONVERGENCE, "Gradient tolerance reached."); break; }
+    if (radius <= o.min_radius) { finish(RCVD_TERM_CONVERGENCE, "Minimum trust region radius reached."); break; }
+    ++iter; stepSuccessful = false;
+    // --- ComputeTrustRegionStep + candidate evaluation, one host sync ---
+    CK(cudaMemsetAsync(p->d_scal, 0, SC_N * sizeof(double), st));
+    CK(cudaMemsetAsync(p->d_fail, 0, sizeof(int), st));
+    CK(cudaEventRecord(p->ev[2], st));
+    k_lm_prepare<<<nblk(Upad), 256, 0, st>>>(p->d_diagH, p->d_S, p->d_g, p->d_lmdiag, p->d_D2, p->d_gs, (int)Upad, reuseDiag ? 1 : 0, radius, o.min_lm_diagonal, o.max_lm_diagonal);
+    p->launches++;
+    reuseDiag = true;
+    if ((rc = factor_solve(p))) return rc;
+    if ((rc = enqueue_model_terms(p))) return rc;
+    CK(cudaEventRecord(p->ev[3], st));
+    double alpha = 1.0;
+    if (!constrained) {
+      if ((rc = enqueue_candidate(p, 1.0, p->d_g))) return rc;
+      if ((rc = enqueue_evaluate(p, p->d_xc, false, false, nullptr, SC_CAND))) return rc;
+      CK(cudaEventRecord(p->ev[4], st));
+    }
+    if ((rc = read_scalars(p))) return rc;
+    sum.linear_ms += ev_ms(p->ev[2], p->ev[3]);
+    if (!constrained) sum.cost_ms += ev_ms(p->ev[3], p->ev[4]);
+    const double gy = p->h_scal[SC_GY], yHy = p->h_scal[SC_YHY];
+    const double modelChange = gy - 0.5 * yHy;
+    const bool ok = (*p->h_fail == 0) && std::isfinite(gy) && std::isfinite(yHy);
+    if (!(ok && modelChange > 0.0)) {
+      if (++invalid >= o.max_consecutive_invalid_steps) { finish(RCVD_TERM_FAILURE, "Number of consecutive invalid steps more than max_num_consecutive_invalid_steps."); break; }
+      radius = radius / decrease; decrease *= 2.0; reuseDiag = true;
+      if (o.verbose) fprintf(stderr, "[rcvd] %4d invalid step (fail=%d model=%g), radius %.3e\n", iter, *p->h_fail, modelChange, radius);
+      continue;
+    }
+    invalid = 0;
+    if (constrained) {
+      // DoLineSearch: Armijo with cubic interpolation along the projected path (ceres defaults)
+      auto trial = [&](double a, ls::Sample& s) -> int {
+        CK(cudaMemsetAsync(p->d_scal, 0, SC_N * sizeof(double), st));
+        int r = enqueue_candidate(p, a, p->d_g); if (r) return r;
+        r = enqueue_evaluate(p, p->d_xc, true, false, p->d_g2, SC_CAND); if (r) return r;
+        k_dot2<<<nblk(Upad), 256, 0, st>>>(p->d_g2, p->d_delta, p->d_g2, p->d_delta, (int)Upad, p->d_scal, SC_GY, SC_YHY);
+        p->launches++;
+        r = read_scalars(p); if (r) return r;
+        s.x = a; s.value = p->h_scal[SC_CAND]; s.valueValid = std::isfinite(s.value);
+        s.gradient = p->h_scal[SC_GY]; s.gradValid = s.valueValid && std::isfinite(s.gradient);
+        return RCVD_OK;
+      };
+      ls::Sample cur, prev{0, 0, 0, false, false};
+      if ((rc = trial(1.0, cur))) return rc;
+      const double gd = p->h_scal[SC_GDOTD], dirMax = p->h_scal[SC_DMAX];
+      ls::Sample init{0.0, xCost, gd, true, true};
+      int lsIter = 0; bool success = true;
+      while (!cur.valueValid || cur.value > xCost + 1e-4 * gd * cur.x) {
+        if (++lsIter >= 20) { success = false; break; }
+        const double lo = 1e-3 * cur.x, hi = 0.6 * cur.x;
+        double ss;
+        if (!cur.valueValid) ss = std::min(std::max(cur.x * 0.5, lo), hi);
+        else { std::vector<ls::Sample> sm{init, cur}; if (prev.valueValid) sm.push_back(prev); ss = ls::minimizeInterpolating(sm, lo, hi); }
+        if (ss * dirMax < 1e-9) { success = false; break; }
+        prev = cur;
+        if ((rc = trial(ss, cur))) return rc;
+      }
+      alpha = success ? cur.x : 1.0;
+      CK(cudaMemsetAsync(p->d_scal, 0, SC_N * sizeof(double), st));
+      if ((rc = enqueue_candidate(p, alpha, p->d_g))) return rc;
+      if ((rc = enqueue_evaluate(p, p->d_xc, false, false, nullptr, SC_CAND))) return rc;
+      if ((rc = read_scalars(p))) return rc;
+    }
+    double candCost = p->h_scal[SC_CAND];
+    if (!std::isfinite(candCost)) candCost = std::numeric_limits<double>::max();
+    const double stepNorm = std::sqrt(p->h_scal[SC_STEP2]);
+    if (stepNorm <= o.parameter_tolerance * (xNorm + o.parameter_tolerance)) { finish(RCVD_TERM_CONVERGENCE, "Parameter tolerance reached."); break; }
+    const double costChange = xCost - candCost;
+    if (std::fabs(costChange) <= o.function_tolerance * xCost) { finish(RCVD_TERM_CONVERGENCE, "Function tolerance reached."); break; }
+    const double relDecrease = (candCost >= std::numeric_limits<double>::max()) ? std::numeric_limits<double>::lowest() : costChange / modelChange;
+    if (relDecrease > o.min_relative_decrease) {
+      std::swap(p->d_x, p->d_xc);
+      if ((rc = full_eval())) return rc;
+      xCost = p->h_scal[SC_COST]; xNorm = std::sqrt(p->h_scal[SC_X2]); gmax = p->h_scal[SC_GMAX];
+      stepSuccessful = true;
+      radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * relDecrease - 1.0, 3));
+      radius = std::min(o.max_radius, radius); decrease = 2.0; reuseDiag = false;
+    } else {
+      radius = radius / decrease; decrease *= 2.0; reuseDiag = true;
+    }
+    if (o.verbose) fprintf(stderr, "[rcvd] %4d %.6e %10.2e %10.2e %10.2e %10.2e %10.2e\n", iter, stepSuccessful ? xCost : candCost, costChange, gmax, stepNorm, relDecrease, radius);
+  }
+  CK(cudaMemcpyAsync(p->d_x, p->d_xsave, U * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  sum.iterations = iter; sum.final_cost = minimumCost;
+  sum.gpu_launches = p->launches - launches0;
+  sum.total_ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+  return RCVD_OK;
+}
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+RCVD_API const char* rcvd_last_error(void) { return g_err.c_str(); }
+RCVD_API int32_t rcvd_abi_version(void) { return 1; }
+RCVD_API int32_t rcvd_frame_stride(const rcvd_config* c) { Layout L; return (c && make_layout(*c, L)) ? L.nf : -1; }
+RCVD_API int32_t rcvd_depth_param_offset(const rcvd_config* c) { Layout L; return (c && make_layout(*c, L)) ? L.offD : -1; }
+RCVD_API int32_t rcvd_spatial_param_offset(const rcvd_config* c) { Layout L; return (c && make_layout(*c, L)) ? L.offS : -1; }
+RCVD_API void rcvd_default_solve_options(rcvd_solve_options* o) {
+  o->max_iterations = 1000; o->verbose = 0; o->function_tolerance = 1e-6; o->gradient_tolerance = 1e-10; o->parameter_tolerance = 1e-8;
+  o->initial_radius = 1e4; o->max_radius = 1e16; o->min_radius = 1e-32; o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6;
+  o->max_lm_diagonal = 1e32; o->max_consecutive_invalid_steps = 5; o->jacobi_scaling = 1;
+}
+
+RCVD_API int32_t rcvd_problem_create(const rcvd_config* cfg, int32_t device, rcvd_problem** out) {
+  if (!cfg || !out) return set_err(RCVD_ERR_INVALID, "null argument");
+  Layout L;
+  if (!make_layout(*cfg, L) || cfg->num_frames <= 0) return set_err(RCVD_ERR_INVALID, "unsupported transform configuration");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev)
+    return set_err(RCVD_ERR_NO_DEVICE, "no usable CUDA device (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device ordinal out of range");
+  CK(cudaSetDevice(device));
+  rcvd_problem* p = new rcvd_problem();
+  p->cfg = *cfg; p->L = L; p->N = cfg->num_frames; p->device = device;
+  e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete p; return set_err(RCVD_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+  *out = p; return RCVD_OK;
+}
+RCVD_API void rcvd_problem_destroy(rcvd_problem* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  free_all(p);
+  for (int i = 0; i < 8; ++i) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
+  if (p->comm && nccl::CommDestroy) nccl::CommDestroy(p->comm);
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+}
+RCVD_API int32_t rcvd_problem_set_frames(rcvd_problem* p, const uint8_t* in_range, const double* median, const double* adaptive) {
+  if (!p) return set_err(RCVD_ERR_INVALID, "null problem");
+  if (in_range) p->in_range.assign(in_range, in_range + p->N); else p->in_range.assign(p->N, 1);
+  if (median) p->median.assign(median, median + p->N); else p->median.assign(p->N, 1.0);
+  if (adaptive && p->cfg.depth_type == RCVD_DEPTH_GRID) p->adaptive.assign(adaptive, adaptive + (size_t)p->N * p->cfg.depth_grid_x * p->cfg.depth_grid_y); else p->adaptive.clear();
+  if (p->cfg.adaptive_deform > 0.0 && p->adaptive.empty()) return set_err(RCVD_ERR_INVALID, "adaptive deformation cost requires node weights");
+  if (p->structure_ready) { cudaSetDevice(p->device); cudaStreamSynchronize(p->stream); CK(cudaMemcpy(p->h_state.data(), p->d_x, p->h_state.size() * sizeof(double), cudaMemcpyDeviceToHost)); }
+  p->structure_ready = false;
+  return RCVD_OK;
+}
+RCVD_API int32_t rcvd_problem_set_constraints(rcvd_problem* p, int32_t np, const int32_t* pf, const int64_t* off, const float* rec) {
+  if (!p || np < 0 || (np > 0 && (!pf || !off))) return set_err(RCVD_ERR_INVALID, "bad constraint arrays");
+  if (p->structure_ready) { cudaSetDevice(p->device); cudaStreamSynchronize(p->stream); CK(cudaMemcpy(p->h_state.data(), p->d_x, p->h_state.size() * sizeof(double), cudaMemcpyDeviceToHost)); }
+  p->pair_frames.assign(pf, pf + 2 * (size_t)np);
+  if (np > 0) p->offsets.assign(off, off + np + 1); else p->offsets.assign(1, 0);
+  for (int i = 0; i < np; ++i) {
+    if (p->offsets[i + 1] < p->offsets[i]) return set_err(RCVD_ERR_INVALID, "offsets must be non-decreasing");
+    if (pf[2 * i] < 0 || pf[2 * i] >= p->N || pf[2 * i + 1] < 0 || pf[2 * i + 1] >= p->N || pf[2 * i] == pf[2 * i + 1]) return set_err(RCVD_ERR_INVALID, "bad frame pair %d", i);
+  }
+  const int64_t C = p->offsets.back();
+  if (C > 0 && !rec) return set_err(RCVD_ERR_INVALID, "null records");
+  p->records_h.assign(rec, rec + (size_t)C * 6);
+  p->structure_ready = false;
+  return RCVD_OK;
+}
+// Global frame-pair graph for multi-GPU runs (every rank must build the same block structure).
+RCVD_API int32_t rcvd_problem_set_structure(rcvd_problem* p, int32_t np, const int32_t* pf) {
+  if (!p) return set_err(RCVD_ERR_INVALID, "null problem");
+  p->struct_pairs.assign(pf, pf + 2 * (size_t)np);
+  p->structure_ready = false;
+  return RCVD_OK;
+}
+RCVD_API int32_t rcvd_nccl_unique_id(uint8_t out[128]) {
+  if (!nccl::load()) return set_err(RCVD_ERR_NCCL, "libnccl.so.2 not found");
+  nccl::UniqueId id; const int r = nccl::GetUniqueId(&id);
+  if (r != 0) return set_err(RCVD_ERR_NCCL, "ncclGetUniqueId failed (%d)", r);
+  memcpy(out, id.internal, 128); return RCVD_OK;
+}
+RCVD_API int32_t rcvd_problem_init_comm(rcvd_problem* p, int32_t nranks, int32_t rank, const uint8_t uid[128]) {
+  if (!p || nranks < 1 || rank < 0 || rank >= nranks) return set_err(RCVD_ERR_INVALID, "bad rank/nranks");
+  if (nranks == 1) { p->nranks = 1; p->rank = 0; return RCVD_OK; }
+  if (!nccl::load()) return set_err(RCVD_ERR_NCCL, "libnccl.so.2 not found");
+  CK(cudaSetDevice(p->device));
+  nccl::UniqueId id; memcpy(id.internal, uid, 128);
+  const int r = nccl::CommInitRank(&p->comm, nranks, id, rank);
+  if (r != 0) return set_err(RCVD_ERR_NCCL, "ncclCommInitRank failed: %s", nccl::GetErrorString ? nccl::GetErrorString(r) : "?");
+  p->nranks = nranks; p->rank = rank; p->structure_ready = false;
+  return RCVD_OK;
+}
+RCVD_API int32_t rcvd_problem_set_state(rcvd_problem* p, const double* x) {
+  if (!p || !x) return set_err(RCVD_ERR_INVALID, "null argument");
+  p->h_state.assign(x, x + (size_t)p->N * p->L.nf); p->state_dirty = true;
+  return RCVD_OK;
+}
+RCVD_API int32_t rcvd_problem_get_state(rcvd_problem* p, double* x) {
+  if (!p || !x) return set_err(RCVD_ERR_INVALID, "null argument");
+  const size_t U = (size_t)p->N * p->L.nf;
+  if (!p->structure_ready || p->state_dirty) { if (p->h_state.size() != U) p->h_state.assign(U, 0.0); memcpy(x, p->h_state.data(), U * sizeof(double)); return RCVD_OK; }
+  CK(cudaSetDevice(p->device));
+  CK(cudaMemcpyAsync(x, p->d_x, U * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  return RCVD_OK;
+}
+RCVD_API int32_t rcvd_evaluate(rcvd_problem* p, double* cost, double* gradient) {
+  if (!p || !cost) return set_err(RCVD_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(p->device));
+  int rc = ensure_ready(p); if (rc) return rc;
+  CK(cudaMemsetAsync(p->d_scal, 0, SC_N * sizeof(double), p->stream));
+  rc = enqueue_evaluate(p, p->d_x, gradient != nullptr, false, p->d_g, SC_COST); if (rc) return rc;
+  rc = read_scalars(p); if (rc) return rc;
+  *cost = p->h_scal[SC_COST];
+  if (gradient) {
+    std::vector<double> g((size_t)p->N * p->L.npad);
+    CK(cudaMemcpy(g.data(), p->d_g, g.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int f = 0; f < p->N; ++f) memcpy(gradient + (size_t)f * p->L.nf, g.data() + (size_t)f * p->L.npad, p->L.nf * sizeof(double));
+  }
+  return RCVD_OK;
+}
+RCVD_API int32_t rcvd_normal_matrix_dense(rcvd_problem* p, double* Hout) {
+  if (!p || !Hout) return set_err(RCVD_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(p->device));
+  int rc = ensure_ready(p); if (rc) return rc;
+  rc = enqueue_evaluate(p, p->d_x, true, true, p->d_g, SC_COST); if (rc) return rc;
+  const size_t U = (size_t)p->N * p->L.nf;
+  double* d_out = nullptr;
+  CK(cudaMalloc((void**)&d_out, U * U * sizeof(double)));
+  CK(cudaMemsetAsync(d_out, 0, U * U * sizeof(double), p->stream));
+  k_h_to_dense<<<dim3(nblk((size_t)p->L.nf * p->L.nf), p->nHblocks), 256, 0, p->stream>>>(p->d_H, p->d_hblocks, p->nHblocks, d_out, p->N, p->L.nf, p->L.npad);
+  cudaError_t e = cudaMemcpyAsync(Hout, d_out, U * U * sizeof(double), cudaMemcpyDeviceToHost, p->stream);
+  cudaStreamSynchronize(p->stream); cudaFree(d_out);
+  if (e != cudaSuccess) return set_err(RCVD_ERR_CUDA, "copy failed: %s", cudaGetErrorString(e));
+  return RCVD_OK;
+}
+// Debug/test: solve (S H S + diag(D2)) y = b with H = J^T J at the current state.
+// S, D2, b, y: N*stride host doubles.
+RCVD_API int32_t rcvd_debug_linear_solve(rcvd_problem* p, const double* S, const double* D2, const double* b, double* y) {
+  if (!p) return set_err(RCVD_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(p->device));
+  int rc = ensure_ready(p); if (rc) return rc;
+  rc = enqueue_evaluate(p, p->d_x, true, true, p->d_g, SC_COST); if (rc) return rc;
+  const int N = p->N, nf = p->L.nf, npad = p->L.npad; const size_t Upad = (size_t)N * npad;
+  std::vector<double> hs(Upad, 1.0), hd(Upad, 1.0), hb(Upad, 0.0);
+  for (int f = 0; f < N; ++f) for (int l = 0; l < nf; ++l) { hs[(size_t)f * npad + l] = S[(size_t)f * nf + l]; hd[(size_t)f * npad + l] = D2[(size_t)f * nf + l]; hb[(size_t)f * npad + l] = b[(size_t)f * nf + l]; }
+  CK(cudaMemcpyAsync(p->d_S, hs.data(), Upad * 8, cudaMemcpyHostToDevice, p->stream));
+  CK(cudaMemcpyAsync(p->d_D2, hd.data(), Upad * 8, cudaMemcpyHostToDevice, p->stream));
+  CK(cudaMemcpyAsync(p->d_gs, hb.data(), Upad * 8, cudaMemcpyHostToDevice, p->stream));
+  CK(cudaMemsetAsync(p->d_fail, 0, sizeof(int), p->stream));
+  rc = factor_solve(p); if (rc) return rc;
+  std::vector<double> hy(Upad);
+  CK(cudaMemcpyAsync(hy.data(), p->d_y, Upad * 8, cudaMemcpyDeviceToHost, p->stream));
+  rc = read_scalars(p); if (rc) return rc;
+  for (int f = 0; f < N; ++f) for (int l = 0; l < nf; ++l) y[(size_t)f * nf + l] = hy[(size_t)f * npad + l];
+  if (*p->h_fail) return set_err(RCVD_ERR_NUMERIC, "factorisation hit a non-positive pivot");
+  return RCVD_OK;
+}
+RCVD_API int32_t rcvd_time_accumulate(rcvd_problem* p, int32_t iters, double* ms) {
+  if (!p || iters <= 0) return set_err(RCVD_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(p->device));
+  int rc = ensure_ready(p); if (rc) return rc;
+  for (int i = 0; i < 2; ++i) if (!p->ev[i]) CK(cudaEventCreate(&p->ev[i]));
+  if ((rc = enqueue_evaluate(p, p->d_x, true, true, p->d_g, SC_COST))) return rc;   // warm-up
+  CK(cudaEventRecord(p->ev[0], p->stream));
+  for (int i = 0; i < iters; ++i) if ((rc = enqueue_evaluate(p, p->d_x, true, true, p->d_g, SC_COST))) return rc;
+  CK(cudaEventRecord(p->ev[1], p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  *ms = ev_ms(p->ev[0], p->ev[1]) / iters;
+  return RCVD_OK;
+}
+RCVD_API int32_t rcvd_time_iteration(rcvd_problem* p, int32_t iters, double radius, double* ms_iter, double* ms_acc, double* ms_lin, double* ms_cost) {
+  if (!p || iters <= 0) return set_err(RCVD_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(p->device));
+  int rc = ensure_ready(p); if (rc) return rc;
+  const int N = p->N, npad = p->L.npad; const size_t Upad = (size_t)N * npad; cudaStream_t st = p->stream;
+  for (int i = 0; i < 8; ++i) if (!p->ev[i]) CK(cudaEventCreate(&p->ev[i]));
+  double ta = 0, tl = 0, tc = 0, tt = 0;
+  for (int it = -1; it < iters; ++it) {   // it == -1: warm-up (also instantiates the graph)
+    CK(cudaMemsetAsync(p->d_scal, 0, SC_N * sizeof(double), st));
+    CK(cudaMemsetAsync(p->d_fail, 0, sizeof(int), st));
+    CK(cudaEventRecord(p->ev[0], st));
+    if ((rc = enqueue_evaluate(p, p->d_x, true, true, p->d_g, SC_COST))) return rc;
+    k_extract_diag<<<nblk(Upad), 256, 0, st>>>(p->d_H, p->d_diagH, N, npad);
+    k_jacobi_scale<<<nblk(Upad), 256, 0, st>>>(p->d_diagH, p->d_S, (int)Upad, 1);
+    CK(cudaEventRecord(p->ev[1], st));
+    k_lm_prepare<<<nblk(Upad), 256, 0, st>>>(p->d_diagH, p->d_S, p->d_g, p->d_lmdiag, p->d_D2, p->d_gs, (int)Upad, 0, radius, 1e-6, 1e32);
+    if ((rc = factor_solve(p))) return rc;
+    if ((rc = enqueue_model_terms(p))) return rc;
+    CK(cudaEventRecord(p->ev[2], st));
+    if ((rc = enqueue_candidate(p, 1.0, p->d_g))) return rc;
+    if ((rc = enqueue_evaluate(p, p->d_xc, false, false, nullptr, SC_CAND))) return rc;
+    CK(cudaEventRecord(p->ev[3], st));
+    if ((rc = read_scalars(p))) return rc;
+    if (it >= 0) { ta += ev_ms(p->ev[0], p->ev[1]); tl += ev_ms(p->ev[1], p->ev[2]); tc += ev_ms(p->ev[2], p->ev[3]); tt += ev_ms(p->ev[0], p->ev[3]); }
+  }
+  *ms_iter = tt / iters; if (ms_acc) *ms_acc = ta / iters; if (ms_lin) *ms_lin = tl / iters; if (ms_cost) *ms_cost = tc / iters;
+  return RCVD_OK;
+}
+RCVD_API int64_t rcvd_launch_count(rcvd_problem* p) { return p ? p->launches : 0; }
+RCVD_API int32_t rcvd_solve(rcvd_problem* p, const rcvd_solve_options* opt, rcvd_solve_summary* summary) {
+  if (!p || !summary) return set_err(RCVD_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(p->device));
+  rcvd_solve_options o; if (opt) o = *opt; else rcvd_default_solve_options(&o);
+  return lm_solve(p, o, *summary);
+}
+// Structure statistics (for DESIGN.md / bench): frames, off-diagonal factor blocks, levels, H blocks, npad.
+RCVD_API int32_t rcvd_structure_info(rcvd_problem* p, int32_t out[8]) {
+  if (!p) return set_err(RCVD_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(p->device));
+  int rc = ensure_ready(p); if (rc) return rc;
+  out[0] = p->N; out[1] = p->nLoff; out[2] = (int)p->levels.size(); out[3] = p->nHblocks; out[4] = p->L.npad; out[5] = p->L.nf; out[6] = p->num_tiles;
+  int upd = 0; for (auto& l : p->levels) upd += l.nupd; out[7] = upd;
+  return RCVD_OK;
+}
+
+// ---- dense transform application (next-row kernels) ----
+template <int MODE>
+static int dense_run(const rcvd_config* cfg, int device, const double* params_in, int nparams, int param_off, const float* src, void* out, size_t out_bytes, int h, int w) {
+  Layout L;
+  if (!cfg || !make_layout(*cfg, L)) return set_err(RCVD_ERR_INVALID, "unsupported transform configuration");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return set_err(RCVD_ERR_NO_DEVICE, "no usable CUDA device; this library has no CPU fallback");
+  CK(cudaSetDevice(device));
+  std::vector<double> pv(L.nf, 0.0);
+  for (int i = 0; i < nparams; ++i) pv[param_off + i] = params_in[i];
+  double* d_p = nullptr; float* d_src = nullptr; void* d_out = nullptr;
+  const size_t n = (size_t)w * h;
+  CK(cudaMalloc((void**)&d_p, pv.size() * 8)); CK(cudaMalloc(&d_out, out_bytes));
+  CK(cudaMemcpy(d_p, pv.data(), pv.size() * 8, cudaMemcpyHostToDevice));
+  if (src) { CK(cudaMalloc((void**)&d_src, n * 4)); CK(cudaMemcpy(d_src, src, n * 4, cudaMemcpyHostToDevice)); }
+  k_dense<MODE><<<nblk(n), 256>>>(*cfg, L, d_p, d_src, d_out, h, w);
+  cudaError_t e = cudaMemcpy(out, d_out, out_bytes, cudaMemcpyDeviceToHost);
+  cudaFree(d_p); cudaFree(d_out); if (d_src) cudaFree(d_src);
+  if (e != cudaSuccess) return set_err(RCVD_ERR_CUDA, "dense kernel failed: %s", cudaGetErrorString(e));
+  return RCVD_OK;
+}
+RCVD_API int32_t rcvd_depth_apply(const rcvd_config* cfg, int32_t device, const double* dp, const float* src, float* dst, int32_t h, int32_t w) {
+  Layout L; if (!cfg || !make_layout(*cfg, L)) return set_err(RCVD_ERR_INVALID, "unsupported transform configuration");
+  return dense_run<0>(cfg, device, dp, L.nd, L.offD, src, dst, (size_t)w * h * 4, h, w);
+}
+RCVD_API int32_t rcvd_depth_param_map(const rcvd_config* cfg, int32_t device, const double* dp, double* out, int32_t h, int32_t w) {
+  Layout L; if (!cfg || !make_layout(*cfg, L)) return set_err(RCVD_ERR_INVALID, "unsupported transform configuration");
+  if (cfg->depth_type != RCVD_DEPTH_GRID) return set_err(RCVD_ERR_INVALID, "Parameter map not implemented for this transform type.");
+  return dense_run<1>(cfg, device, dp, L.nd, L.offD, nullptr, out, (size_t)w * h * L.k * 8, h, w);
+}
+RCVD_API int32_t rcvd_spatial_warp(const rcvd_config* cfg, int32_t device, const double* sp, float* out, int32_t h, int32_t w) {
+  Layout L; if (!cfg || !make_layout(*cfg, L)) return set_err(RCVD_ERR_INVALID, "unsupported transform configuration");
+  return dense_run<2>(cfg, device, sp, L.ns, L.offS, nullptr, out, (size_t)w * h * 8, h, w);
+}

@@ -1,0 +1,318 @@
+// rcvd_eval.cuh -- residual / Jacobian / normal-equation accumulation kernels.
+//
+// K1 gn_accumulate : per flow constraint, StaticSceneCost residual + analytic Jacobian
+//                    + Cauchy correction + scatter of J^T J and J^T r   (reference hot loop D,
+//                    lib/PoseOptimizer.cpp:237-308 evaluated by Ceres autodiff at :1198)
+// K2 cost_only     : residual + rho only, for LM step acceptance
+// K3 regularisers  : scale / deform / spatial / focal / position rows (:488-656, :1341-1549)
+#pragma once
+#include "rcvd_device.cuh"
+
+namespace rcvd {
+
+constexpr int kTile = 128;          // constraints per CTA tile (all from one directed pair)
+constexpr int kMaxEntries = 144;    // 2 * (6 + 1 + 16*2 + 16*2) + slack
+
+struct DevProblem {
+  rcvd_config cfg;
+  Layout L;
+  int N;
+  int num_tiles;
+  int64_t num_constraints;
+  const float* records;        // [C][6]
+  const int32_t* tile_pair;    // [T]
+  const int64_t* tile_begin;   // [T]
+  const int32_t* tile_count;   // [T]
+  const int32_t* pair_frames;  // [P][2]
+  const int32_t* blk_of;       // [N*N]: (fa,fb) -> H block id*2 + (fa is the row side), -1 if absent
+  const uint8_t* in_range;     // [N]
+  const double* median;        // [N]
+  const double* adaptive;      // [N*G] or null
+  const float* scale_locs;     // [M][2]
+  int num_scale_locs;
+  int rank, nranks;            // regulariser rows are evaluated by rank f % nranks
+};
+
+__device__ __forceinline__ bool is_const_local(const rcvd_config& c, const Layout& L, int l) {
+  if (l < 6) return c.fix_poses != 0;
+  if (l == 6) return c.intr_opt == RCVD_INTR_FIXED;
+  if (l < L.offS) return c.fix_depth_xforms != 0;
+  return c.fix_spatial_xforms != 0;
+}
+
+// Adds v to H(fa:la, fb:lb).  Diagonal blocks store the lower triangle only.
+__device__ __forceinline__ void add_h(const DevProblem& p, double* H, int fa, int la, int fb, int lb, double v) {
+  const int np = p.L.npad;
+  if (fa == fb) {
+    const int i = max(la, lb), j = min(la, lb);
+    red_add(H + (size_t)fa * np * np + (size_t)i * np + j, v);
+  } else {
+    const int enc = p.blk_of[fa * p.N + fb];
+    const size_t base = (size_t)(enc >> 1) * np * np;
+    if (enc & 1) red_add(H + base + (size_t)la * np + lb, v);
+    else red_add(H + base + (size_t)lb * np + la, v);
+  }
+}
+
+struct StaticEval {
+  double r[3];
+  double rho0, scale;
+};
+
+// Shared front end of K1/K2: loads the record, gathers, evaluates residual (+ local Jacobian).
+template <bool JAC>
+__device__ __forceinline__ void eval_constraint(const DevProblem& p, const double* __restrict__ x, int f0, int f1,
+                                                const float* __restrict__ rec, Gather& dg0, Gather& sg0, Gather& dg1, Gather& sg1,
+                                                StaticEval& ev, double* Jl) {
+  const rcvd_config& c = p.cfg; const Layout& L = p.L;
+  const double* pf0 = x + (size_t)f0 * L.nf; const double* pf1 = x + (size_t)f1 * L.nf;
+  ObsIn o0{rec[0], rec[1], rec[2]}, o1{rec[3], rec[4], rec[5]};
+  gather_depth(c, o0.ndcx, o0.ndcy, dg0); gather_depth(c, o1.ndcx, o1.ndcy, dg1);
+  gather_spatial(c, o0.ndcx, o0.ndcy, sg0); gather_spatial(c, o1.ndcx, o1.ndcy, sg1);
+  double phi0, phi1;
+  if (c.intr_opt == RCVD_INTR_SHARED) phi0 = phi1 = x[6];          // &poseParams_[0][6], lib/PoseOptimizer.cpp:1226
+  else if (c.intr_opt == RCVD_INTR_PER_FRAME) { phi0 = pf0[6]; phi1 = pf1[6]; }
+  else phi0 = phi1 = c.fixed_vfocal;
+  const double D0 = depth_value(c, L, dg0, o0.depth, pf0), D1 = depth_value(c, L, dg1, o1.depth, pf1);
+  double u0[2], u1[2];
+  warp_value(L, sg0, pf0, u0); warp_value(L, sg1, pf1, u1);
+  static_scene<JAC>(c, pf0, phi0, D0, u0, pf1, phi1, D1, u1, o0, o1, ev.r, Jl);
+  const double s = ev.r[0] * ev.r[0] + ev.r[1] * ev.r[1] + ev.r[2] * ev.r[2];
+  double rho1;
+  robust_loss(c, s, ev.rho0, rho1);
+  ev.scale = sqrt(rho1);    // Corrector with rho'' <= 0: residual and Jacobian scaled by sqrt(rho')
+}
+
+// Block-level sum -> partial[blockIdx.x]  (deterministic two-stage cost reduction)
+__device__ __forceinline__ void block_store_sum(double v, double* partial) {
+  __shared__ double red[32];
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    double t = lane < nw ? red[lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) *partial = t;
+  }
+}
+
+// K2: cost only.
+__global__ void __launch_bounds__(kTile) k_cost_static(DevProblem p, const double* __restrict__ x, double* __restrict__ partial) {
+  const int t = blockIdx.x;
+  const int pr = p.tile_pair[t];
+  const int f0 = p.pair_frames[2 * pr], f1 = p.pair_frames[2 * pr + 1];
+  double cost = 0.0;
+  if ((int)threadIdx.x < p.tile_count[t]) {
+    const float* rec = p.records + (size_t)(p.tile_begin[t] + threadIdx.x) * 6;
+    Gather dg0, sg0, dg1, sg1; StaticEval ev;
+    eval_constraint<false>(p, x, f0, f1, rec, dg0, sg0, dg1, sg1, ev, nullptr);
+    cost = 0.5 * ev.rho0;
+  }
+  block_store_sum(cost, partial + t);
+}
+
+// K1 (generic path): every transform / intrinsics mode; scatter with L2 reductions.
+// WANT_H = false gives the gradient-only evaluation used by the bounded line search.
+template <bool WANT_H>
+__global__ void __launch_bounds__(kTile) k_accumulate_generic(DevProblem p, const double* __restrict__ x, double* __restrict__ H,
+                                                               double* __restrict__ g, double* __restrict__ partial) {
+  const rcvd_config& c = p.cfg; const Layout& L = p.L;
+  const int t = blockIdx.x;
+  const int pr = p.tile_pair[t];
+  const int f0 = p.pair_frames[2 * pr], f1 = p.pair_frames[2 * pr + 1];
+  double cost = 0.0;
+  if ((int)threadIdx.x < p.tile_count[t]) {
+    const float* rec = p.records + (size_t)(p.tile_begin[t] + threadIdx.x) * 6;
+    Gather dg0, sg0, dg1, sg1; StaticEval ev; double Jl[60];
+    eval_constraint<true>(p, x, f0, f1, rec, dg0, sg0, dg1, sg1, ev, Jl);
+    cost = 0.5 * ev.rho0;
+    const double sc = ev.scale;
+    const double r0 = ev.r[0] * sc, r1 = ev.r[1] * sc, r2 = ev.r[2] * sc;
+    // expanded columns: (frame, local column, 3-vector)
+    int ef[kMaxEntries]; short el[kMaxEntries]; double ej[kMaxEntries][3];
+    int E = 0;
+    auto push = [&](int f, int l, double a0, double a1, double a2) {
+      if (is_const_local(c, L, l)) return;
+      ef[E] = f; el[E] = (short)l; ej[E][0] = a0 * sc; ej[E][1] = a1 * sc; ej[E][2] = a2 * sc; ++E;
+    };
+    for (int side = 0; side < 2; ++side) {
+      const int f = side ? f1 : f0; const int o = side * 10;
+      const Gather& dg = side ? dg1 : dg0; const Gather& sg = side ? sg1 : sg0;
+      const double src = (double)(side ? rec[5] : rec[2]);
+      for (int q = 0; q < 6; ++q) push(f, q, Jl[o + q], Jl[20 + o + q], Jl[40 + o + q]);
+      if (c.intr_opt == RCVD_INTR_PER_FRAME) push(f, 6, Jl[o + 6], Jl[20 + o + 6], Jl[40 + o + 6]);
+      for (int q = 0; q < dg.n; ++q) {
+        const double w = dg.w[q];
+        push(f, L.offD + dg.idx[q] * L.k, Jl[o + 7] * w * src, Jl[20 + o + 7] * w * src, Jl[40 + o + 7] * w * src);
+        if (L.k == 2) push(f, L.offD + dg.idx[q] * 2 + 1, Jl[o + 7] * w, Jl[20 + o + 7] * w, Jl[40 + o + 7] * w);
+      }
+      for (int q = 0; q < sg.n; ++q) {
+        const double w = sg.w[q];
+        push(f, L.offS + sg.idx[q] * 2, Jl[o + 8] * w, Jl[20 + o + 8] * w, Jl[40 + o + 8] * w);
+        push(f, L.offS + sg.idx[q] * 2 + 1, Jl[o + 9] * w, Jl[20 + o + 9] * w, Jl[40 + o + 9] * w);
+      }
+    }
+    if (c.intr_opt == RCVD_INTR_SHARED) push(0, 6, Jl[6] + Jl[16], Jl[26] + Jl[36], Jl[46] + Jl[56]);
+    const int np = L.npad;
+    for (int a = 0; a < E; ++a) {
+      const double a0 = ej[a][0], a1 = ej[a][1], a2 = ej[a][2];
+      red_add(g + (size_t)ef[a] * np + el[a], a0 * r0 + a1 * r1 + a2 * r2);
+      if (WANT_H) {
+        for (int b = 0; b <= a; ++b) {
+          const double v = a0 * ej[b][0] + a1 * ej[b][1] + a2 * ej[b][2];
+          add_h(p, H, ef[a], el[a], ef[b], el[b], v);
+        }
+      }
+    }
+  }
+  block_store_sum(cost, partial + t);
+}
+
+// Marks parameters referenced by at least one residual block (the Ceres program's
+// parameter set): used for |x| / |step| norms.  mask has npad stride.
+__global__ void __launch_bounds__(kTile) k_mark_static(DevProblem p, uint8_t* __restrict__ mask) {
+  const rcvd_config& c = p.cfg; const Layout& L = p.L;
+  const int t = blockIdx.x;
+  if ((int)threadIdx.x >= p.tile_count[t]) return;
+  const int pr = p.tile_pair[t];
+  const int fr[2] = {p.pair_frames[2 * pr], p.pair_frames[2 * pr + 1]};
+  const float* rec = p.records + (size_t)(p.tile_begin[t] + threadIdx.x) * 6;
+  const int np = L.npad;
+  for (int side = 0; side < 2; ++side) {
+    Gather dg, sg;
+    gather_depth(c, rec[side * 3], rec[side * 3 + 1], dg); gather_spatial(c, rec[side * 3], rec[side * 3 + 1], sg);
+    uint8_t* m = mask + (size_t)fr[side] * np;
+    for (int q = 0; q < 6; ++q) m[q] = 1;
+    if (c.intr_opt == RCVD_INTR_PER_FRAME) m[6] = 1;
+    for (int q = 0; q < dg.n; ++q) for (int j = 0; j < L.k; ++j) m[L.offD + dg.idx[q] * L.k + j] = 1;
+    for (int q = 0; q < sg.n; ++q) { m[L.offS + sg.idx[q] * 2] = 1; m[L.offS + sg.idx[q] * 2 + 1] = 1; }
+  }
+  if (c.intr_opt == RCVD_INTR_SHARED) mask[6] = 1;
+}
+
+// --- K3: regulariser rows ---------------------------------------------------
+struct RegCounts { int scale, deform, spatial, focal, per_frame; int position_rows; int total; };
+
+__host__ __device__ inline RegCounts reg_counts(const rcvd_config& c, const Layout& L, int N, int nscale) {
+  RegCounts r;
+  r.scale = (c.scale_reg > 0.0 && !c.fix_depth_xforms && (c.depth_type == RCVD_DEPTH_GLOBAL || c.depth_type == RCVD_DEPTH_GRID)) ? nscale : 0;
+  r.deform = (c.depth_deform_reg > 0.0 && c.depth_type == RCVD_DEPTH_GRID)
+                 ? ((c.depth_grid_x - 1) * c.depth_grid_y + c.depth_grid_x * (c.depth_grid_y - 1)) * L.k : 0;
+  r.spatial = (c.spatial_deform_reg > 0.0) ? L.ns : 0;
+  r.focal = (c.focal_reg > 0.0 && c.intr_opt != RCVD_INTR_FIXED) ? 1 : 0;
+  r.per_frame = r.scale + r.deform + r.spatial + r.focal;
+  r.position_rows = (c.position_reg > 0.0 && N >= 3) ? (N - 2) * 3 : 0;
+  r.total = r.per_frame * N + r.position_rows;
+  return r;
+}
+
+// MODE 0: cost only, 1: cost + gradient + H, 2: mark active, 3: cost + gradient
+template <int MODE>
+__global__ void __launch_bounds__(128) k_regularisers(DevProblem p, RegCounts rc, const double* __restrict__ x, double* __restrict__ H,
+                                                      double* __restrict__ g, double* __restrict__ partial, uint8_t* __restrict__ mask,
+                                                      int first_frame, int last_frame) {
+  const rcvd_config& c = p.cfg; const Layout& L = p.L;
+  const int np = L.npad;
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  double cost = 0.0;
+  int nent = 0; int ef[3] = {0, 0, 0}; int el[32]; double ed[32]; int efr[32];   // entries (frame, local, derivative)
+  double r = 0.0; bool valid = false;
+  if (id < rc.per_frame * p.N) {
+    const int f = id / rc.per_frame; int k = id % rc.per_frame;
+    const bool mine = (p.nranks <= 1) || (f % p.nranks == p.rank);
+    if (p.in_range[f] && mine) {
+      const double* pf = x + (size_t)f * L.nf;
+      ef[0] = f;
+      if (k < rc.scale) {
+        // TargetDisparityCost (lib/PoseOptimizer.cpp:488-517) on the lattice of :1382-1385, ScaledLoss(scaleReg)
+        const double sw = sqrt(c.scale_reg);
+        const float med = (float)p.median[f];
+        Gather gth; gather_depth(c, p.scale_locs[2 * k], p.scale_locs[2 * k + 1], gth);
+        const double depth = depth_value(c, L, gth, med, pf);
+        const bool clamped = depth < 1e-6;
+        r = (1.0 / (clamped ? 1e-6 : depth) - 1.0) * sw;
+        const double dd = clamped ? 0.0 : -1.0 / (depth * depth);
+        for (int q = 0; q < gth.n; ++q) {
+          el[nent] = L.offD + gth.idx[q] * L.k; ed[nent] = dd * gth.w[q] * (double)med * sw; efr[nent] = f; ++nent;
+          if (L.k == 2) { el[nent] = L.offD + gth.idx[q] * 2 + 1; ed[nent] = dd * gth.w[q] * sw; efr[nent] = f; ++nent; }
+        }
+        valid = true;
+      } else if ((k -= rc.scale) < rc.deform) {
+        // computeGridDeformationCost (lib/DepthMapTransform.cpp:631-667) * weight (DeformationCost / Adaptive, :536-656)
+        const int gx = c.depth_grid_x, gy = c.depth_grid_y;
+        const int comp = k % L.k; const int e = k / L.k;
+        int a, b;
+        const int nh = (gx - 1) * gy;
+        if (e < nh) { const int yy = e / (gx - 1), xx = e % (gx - 1) + 1; a = xx + yy * gx; b = a - 1; }
+        else { const int e2 = e - nh; const int yy = e2 / gx + 1, xx = e2 % gx; a = xx + yy * gx; b = a - gx; }
+        double w = c.depth_deform_reg;
+        if (c.adaptive_deform > 0.0 && p.adaptive) {
+          const double* aw = p.adaptive + (size_t)f * gx * gy;
+          w = c.depth_deform_reg + fmax(aw[a], aw[b]) * c.adaptive_deform;
+        }
+        const int la = L.offD + a * L.k + comp, lb = L.offD + b * L.k + comp;
+        const double va = pf[la], vb = pf[lb];
+        const double aa = va < 0.0 ? -va : va, ab = vb < 0.0 ? -vb : vb;
+        const bool useB = ab < aa;               // min(abs(this), abs(that)) = (that < this) ? that : this
+        const double m = useB ? ab : aa;
+        r = (va - vb) / m * w;
+        double da = 1.0 / m, db = -1.0 / m;
+        if (useB) db += -(va - vb) / (m * m) * (vb < 0.0 ? -1.0 : 1.0);
+        else da += -(va - vb) / (m * m) * (va < 0.0 ? -1.0 : 1.0);
+        el[0] = la; ed[0] = da * w; efr[0] = f; el[1] = lb; ed[1] = db * w; efr[1] = f; nent = 2;
+        valid = true;
+      } else if ((k -= rc.deform) < rc.spatial) {
+        // paramsToResiduals (lib/DepthMapTransform.cpp:61-70) * spatialDeformReg
+        r = pf[L.offS + k] * c.spatial_deform_reg; el[0] = L.offS + k; ed[0] = c.spatial_deform_reg; efr[0] = f; nent = 1; valid = true;
+      } else {
+        // TargetFocalCost (lib/PoseOptimizer.cpp:520-533), ScaledLoss(focalReg)
+        const double sw = sqrt(c.focal_reg);
+        r = (pf[6] - c.focal_target) * sw; el[0] = 6; ed[0] = sw; efr[0] = f; nent = 1; valid = true;
+      }
+    }
+  } else if (id < rc.total) {
+    // ParameterRegularizationCost (lib/PoseOptimizer.cpp:464-483) over in-range triplets (:1420-1426)
+    const int k = id - rc.per_frame * p.N;
+    const int f = k / 3, i = k % 3;
+    const bool mine = (p.nranks <= 1) || (f % p.nranks == p.rank);
+    if (mine && f >= first_frame && f < last_frame - 1 && p.in_range[f] && p.in_range[f + 1] && p.in_range[f + 2]) {
+      const double sw = sqrt(c.position_reg);
+      r = (x[(size_t)f * L.nf + i] - 2.0 * x[(size_t)(f + 1) * L.nf + i] + x[(size_t)(f + 2) * L.nf + i]) * sw;
+      el[0] = i; ed[0] = sw; efr[0] = f; el[1] = i; ed[1] = -2.0 * sw; efr[1] = f + 1; el[2] = i; ed[2] = sw; efr[2] = f + 2; nent = 3;
+      valid = true;
+    }
+  }
+  if (valid) {
+    cost = 0.5 * r * r;
+    if (MODE == 2) { for (int a = 0; a < nent; ++a) mask[(size_t)efr[a] * np + el[a]] = 1; }
+    if (MODE == 1 || MODE == 3) {
+      for (int a = 0; a < nent; ++a) if (is_const_local(c, L, el[a])) ed[a] = 0.0;
+      for (int a = 0; a < nent; ++a) {
+        if (ed[a] == 0.0) continue;
+        red_add(g + (size_t)efr[a] * np + el[a], ed[a] * r);
+        if (MODE == 1) for (int b = 0; b <= a; ++b) if (ed[b] != 0.0) add_h(p, H, efr[a], el[a], efr[b], el[b], ed[a] * ed[b]);
+      }
+    }
+  }
+  if (MODE != 2) block_store_sum(cost, partial + blockIdx.x);
+}
+
+// Final deterministic reduction of the per-block partial costs: out[slot] = sum(partial[0..n))
+__global__ void __launch_bounds__(1024) k_reduce_partials(const double* __restrict__ partial, int n, double* __restrict__ out, int slot) {
+  __shared__ double red[32];
+  double v = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v += partial[i];
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    double t = lane < (int)(blockDim.x >> 5) ? red[lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) out[slot] = t;
+  }
+}
+
+}  // namespace rcvd

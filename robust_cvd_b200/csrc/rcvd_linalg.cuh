@@ -1,0 +1,377 @@
+// rcvd_linalg.cuh -- exact block-sparse Cholesky of the damped normal equations on device.
+//
+// The reference solves (J_s^T J_s + D^2) y = J_s^T r with Ceres' SPARSE_NORMAL_CHOLESKY
+// (lib/PoseOptimizer.cpp:956).  Here the matrix is block-sparse over frames (one dense
+// npad x npad block per coupled frame pair, npad = per-frame unknowns rounded to 16);
+// a fill-reducing elimination order and level schedule are computed once on the host and
+// the numeric work runs as batched per-level kernels:
+//   k_potrf   (one CTA per diagonal block)      L_kk, plus 16x16 diagonal-tile inverses
+//   k_trinv   (one CTA per 16-column panel)     inv(L_kk)
+//   k_gemm_nt (fp64 tensor-core DMMA, 64x64)    X_rk = A_rk inv(L_kk)^T ;  A_rc -= X_rk X_ck^T
+// and the triangular solves become GEMVs with inv(L_kk).
+#pragma once
+#include "rcvd_device.cuh"
+
+namespace rcvd {
+
+// ---------------------------------------------------------------------------
+// k_potrf: in-place lower Cholesky of diagonal blocks; right-looking, 16-wide panels.
+// ---------------------------------------------------------------------------
+constexpr int kPotrfThreads = 256;
+
+__global__ void __launch_bounds__(kPotrfThreads) k_potrf(double* __restrict__ Lb, double* __restrict__ invT,
+                                                          const int* __restrict__ frames, int npad, int* __restrict__ fail) {
+  extern __shared__ double panel[];           // [npad][17] (padded rows: conflict-free column walks)
+  __shared__ double D[16][17];
+  __shared__ double Di[16][17];
+  const int frame = frames[blockIdx.x];
+  double* A = Lb + (size_t)frame * npad * npad;
+  double* iT = invT + (size_t)frame * npad * 16;   // nt tiles of 16x16
+  const int nt = npad / 16;
+  const int tid = threadIdx.x;
+  for (int jb = 0; jb < nt; ++jb) {
+    const int j0 = jb * 16;
+    {
+      const int r = tid >> 4, cc = tid & 15;
+      D[r][cc] = (cc <= r) ? A[(size_t)(j0 + r) * npad + j0 + cc] : 0.0;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      // unblocked Cholesky of the 16x16 tile, lane i owns row i
+      const int i = tid;
+      for (int j = 0; j < 16; ++j) {
+        if (i == j) {
+          double d = D[j][j];
+          for (int q = 0; q < j; ++q) d -= D[j][q] * D[j][q];
+          if (!(d > 0.0) || !isfinite(d)) { *fail = 1; d = 1.0; }
+          D[j][j] = sqrt(d);
+        }
+        __syncwarp();
+        if (i > j && i < 16) {
+          double s = D[i][j];
+          for (int q = 0; q < j; ++q) s -= D[i][q] * D[j][q];
+          D[i][j] = s / D[j][j];
+        }
+        __syncwarp();
+      }
+      // inverse of the lower-triangular tile: lane c computes column c
+      if (i < 16) {
+        const int cidx = i;
+        double xcol[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          double s = (r == cidx) ? 1.0 : 0.0;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) if (q < r) s -= D[r][q] * xcol[q];
+          xcol[r] = (r < cidx) ? 0.0 : s / D[r][r];
+        }
+#pragma unroll
+        for (int r = 0; r < 16; ++r) Di[r][cidx] = xcol[r];
+      }
+    }
+    __syncthreads();
+    {
+      const int r = tid >> 4, cc = tid & 15;
+      A[(size_t)(j0 + r) * npad + j0 + cc] = D[r][cc];
+      iT[(size_t)jb * 256 + r * 16 + cc] = Di[r][cc];
+    }
+    // panel solve: X[i][:] = A[i][j0..j0+15] * Di^T for rows below the tile
+    const int below = npad - (j0 + 16);
+    for (int rr = tid; rr < below; rr += kPotrfThreads) {
+      const int i = j0 + 16 + rr;
+      double a[16], xo[16];
+      double* row = A + (size_t)i * npad + j0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) a[q] = row[q];
+#pragma unroll
+      for (int cc = 0; cc < 16; ++cc) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) if (q <= cc) s += a[q] * Di[cc][q];
+        xo[cc] = s;
+      }
+#pragma unroll
+      for (int q = 0; q < 16; ++q) { row[q] = xo[q]; panel[(size_t)rr * 17 + q] = xo[q]; }
+    }
+    __syncthreads();
+    // trailing update of the lower tiles: A[ti][tj] -= P[ti] P[tj]^T, jb < tj <= ti
+    const int m = nt - jb - 1;
+    const int ntiles = m * (m + 1) / 2;
+    const int warp = tid >> 5, lane = tid & 31, nw = kPotrfThreads / 32;
+    for (int tl = warp; tl < ntiles; tl += nw) {
+      // unrank (ti >= tj) from tl
+      int ti = (int)((sqrt(8.0 * tl + 1.0) - 1.0) * 0.5);
+      while ((ti + 1) * (ti + 2) / 2 <= tl) ++ti;
+      while (ti * (ti + 1) / 2 > tl) --ti;
+      const int tj = tl - ti * (ti + 1) / 2;
+      const int r = lane >> 1, c0 = (lane & 1) * 8;
+      const double* pa = panel + (size_t)(ti * 16 + r) * 17;
+      double acc[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const double av = pa[q];
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) acc[cc] += av * panel[(size_t)(tj * 16 + c0 + cc) * 17 + q];
+      }
+      double* out = A + (size_t)(j0 + 16 + ti * 16 + r) * npad + j0 + 16 + tj * 16 + c0;
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) out[cc] -= acc[cc];
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// k_trinv: inv(L_kk), one CTA per 16-column panel j; forward substitution by tiles using the
+// diagonal-tile inverses from k_potrf.  Writes the full npad x npad block (zeros above).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_trinv(const double* __restrict__ Lb, const double* __restrict__ invT, double* __restrict__ invL,
+                                                const int* __restrict__ frames, int npad) {
+  extern __shared__ double Z[];   // [nt][16][16] tile column j of the inverse (only tiles >= j used)
+  __shared__ double W[16][17];
+  const int frame = frames[blockIdx.y];
+  const int j = blockIdx.x;
+  const int nt = npad / 16;
+  const double* A = Lb + (size_t)frame * npad * npad;
+  const double* iT = invT + (size_t)frame * npad * 16;
+  double* out = invL + (size_t)frame * npad * npad;
+  const int tid = threadIdx.x, r = tid >> 4, c = tid & 15;
+  for (int i = 0; i < j; ++i) out[(size_t)(i * 16 + r) * npad + j * 16 + c] = 0.0;
+  Z[(size_t)j * 256 + tid] = iT[(size_t)j * 256 + tid];
+  out[(size_t)(j * 16 + r) * npad + j * 16 + c] = Z[(size_t)j * 256 + tid];
+  __syncthreads();
+  for (int i = j + 1; i < nt; ++i) {
+    double s = 0.0;
+    const double* Lrow = A + (size_t)(i * 16 + r) * npad;
+    for (int p = j; p < i; ++p) {
+      const double* zp = Z + (size_t)p * 256;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) s += Lrow[p * 16 + q] * zp[q * 16 + c];
+    }
+    W[r][c] = s;
+    __syncthreads();
+    double zv = 0.0;
+    const double* ti = iT + (size_t)i * 256;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) zv -= ti[r * 16 + q] * W[q][c];
+    Z[(size_t)i * 256 + tid] = zv;
+    out[(size_t)(i * 16 + r) * npad + j * 16 + c] = zv;
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// k_gemm_nt: dst[t.dst] = beta*dst + alpha * sum_p A[pairs[p].x] * B[pairs[p].y]^T
+// fp64 tensor cores (mma.sync m8n8k4 -> DMMA), CTA tile 64x64, 4 warps of 32x32,
+// K staged 16 at a time through a cp.async double buffer.
+// ---------------------------------------------------------------------------
+struct GemmTask { int dst; int first; int count; int lower_only; };
+
+constexpr int kGemmLd = 20;   // padded leading dimension of the 64x16 smem tiles (conflict-free DMMA fragment loads)
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(128) k_gemm_nt(double* __restrict__ dst, const double* __restrict__ Abase, const double* __restrict__ Bbase,
+                                                  const GemmTask* __restrict__ tasks, const int2* __restrict__ pairs,
+                                                  int npad, double alpha, double beta) {
+  __shared__ __align__(16) double As[2][64 * kGemmLd];
+  __shared__ __align__(16) double Bs[2][64 * kGemmLd];
+  const GemmTask task = tasks[blockIdx.z];
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  if (task.lower_only && n0 > m0) return;   // symmetric target: tiles strictly above the diagonal are never read
+  const size_t bs = (size_t)npad * npad;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  const int g = lane >> 2, t = lane & 3;
+  const int kchunks = npad / 16;
+  const int total = task.count * kchunks;
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+  auto load_stage = [&](int st, int kk) {
+    const int2 pr = pairs[task.first + kk / kchunks];
+    const int k0 = (kk % kchunks) * 16;
+    const double* Ag = Abase + (size_t)pr.x * bs + k0;
+    const double* Bg = Bbase + (size_t)pr.y * bs + k0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int cidx = tid + q * 128;
+      const int row = cidx >> 3, kc = (cidx & 7) * 2;
+      const bool va = (m0 + row) < npad, vb = (n0 + row) < npad;
+      cp_async16(&As[st][row * kGemmLd + kc], Ag + (size_t)(va ? m0 + row : 0) * npad + kc, va);
+      cp_async16(&Bs[st][row * kGemmLd + kc], Bg + (size_t)(vb ? n0 + row : 0) * npad + kc, vb);
+    }
+    cp_async_commit();
+  };
+
+  if (total > 0) load_stage(0, 0);
+  for (int kk = 0; kk < total; ++kk) {
+    const int st = kk & 1;
+    if (kk + 1 < total) { load_stage(st ^ 1, kk + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+    const double* as = As[st]; const double* bsm = Bs[st];
+#pragma unroll
+    for (int k4 = 0; k4 < 4; ++k4) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) af[i] = as[(wm + i * 8 + g) * kGemmLd + k4 * 4 + t];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bf[j] = bsm[(wn + j * 8 + g) * kGemmLd + k4 * 4 + t];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+    __syncthreads();
+  }
+  double* C = dst + (size_t)task.dst * bs;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = m0 + wm + i * 8 + g;
+    if (row >= npad) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = n0 + wn + j * 8 + 2 * t;
+      if (col >= npad) continue;
+      double2* ptr = reinterpret_cast<double2*>(C + (size_t)row * npad + col);
+      double2 o;
+      if (beta != 0.0) { o = *ptr; o.x = beta * o.x + alpha * acc[i][j][0]; o.y = beta * o.y + alpha * acc[i][j][1]; }
+      else { o.x = alpha * acc[i][j][0]; o.y = alpha * acc[i][j][1]; }
+      *ptr = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Triangular solves as GEMVs with inv(L_kk); vectors have npad stride per frame.
+// ---------------------------------------------------------------------------
+// y_k = inv(L_kk) rhs_k   (grid: (ceil(npad/8), frames in level), 256 threads = 8 warps, one row per warp)
+__global__ void __launch_bounds__(256) k_fwd_diag(const double* __restrict__ invL, const double* __restrict__ rhs, double* __restrict__ y,
+                                                   const int* __restrict__ frames, int npad) {
+  const int frame = frames[blockIdx.y];
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= npad) return;
+  const double* M = invL + (size_t)frame * npad * npad + (size_t)row * npad;
+  const double* b = rhs + (size_t)frame * npad;
+  double s = 0.0;
+  for (int q = lane; q <= row; q += 32) s += M[q] * b[q];
+  s = warp_sum(s);
+  if (lane == 0) y[(size_t)frame * npad + row] = s;
+}
+struct SolveTask { int blk; int r; int k; };   // off-diagonal factor block index (into T), row frame, column frame
+// rhs_r -= T_rk y_k      (grid: (ceil(npad/8), tasks in level))
+__global__ void __launch_bounds__(256) k_fwd_update(const double* __restrict__ T, const double* __restrict__ y, double* __restrict__ rhs,
+                                                     const SolveTask* __restrict__ tasks, int npad) {
+  const SolveTask tk = tasks[blockIdx.y];
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= npad) return;
+  const double* M = T + (size_t)tk.blk * npad * npad + (size_t)row * npad;
+  const double* v = y + (size_t)tk.k * npad;
+  double s = 0.0;
+  for (int q = lane; q < npad; q += 32) s += M[q] * v[q];
+  s = warp_sum(s);
+  if (lane == 0) red_add(rhs + (size_t)tk.r * npad + row, -s);
+}
+// y_k -= sum_{r in struct(k)} T_rk^T x_r   (grid: (ceil(npad/256), frames in level)); CSR over frames
+__global__ void __launch_bounds__(256) k_bwd_update(const double* __restrict__ T, const double* __restrict__ x, double* __restrict__ y,
+                                                     const int* __restrict__ frames, const int* __restrict__ col_ptr,
+                                                     const SolveTask* __restrict__ col_tasks, int npad) {
+  const int frame = frames[blockIdx.y];
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= npad) return;
+  double acc = 0.0;
+  for (int e = col_ptr[frame]; e < col_ptr[frame + 1]; ++e) {
+    const SolveTask tk = col_tasks[e];
+    const double* M = T + (size_t)tk.blk * npad * npad + j;
+    const double* xr = x + (size_t)tk.r * npad;
+    for (int i = 0; i < npad; ++i) acc += M[(size_t)i * npad] * xr[i];
+  }
+  y[(size_t)frame * npad + j] -= acc;
+}
+// x_k = inv(L_kk)^T y_k    (grid: (ceil(npad/256), frames in level))
+__global__ void __launch_bounds__(256) k_bwd_diag(const double* __restrict__ invL, const double* __restrict__ y, double* __restrict__ x,
+                                                   const int* __restrict__ frames, int npad) {
+  const int frame = frames[blockIdx.y];
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= npad) return;
+  const double* M = invL + (size_t)frame * npad * npad + j;
+  const double* v = y + (size_t)frame * npad;
+  double acc = 0.0;
+  for (int i = j; i < npad; ++i) acc += M[(size_t)i * npad] * v[i];
+  x[(size_t)frame * npad + j] = acc;
+}
+
+// ---------------------------------------------------------------------------
+// Factor load: L <- S H S + D2 (lower triangle of diagonal blocks, pad diagonal = 1)
+// grid: (ceil(npad*npad/256), H blocks)
+// ---------------------------------------------------------------------------
+struct HBlock { int lblk; int r; int c; };   // H list: lblk = destination block in L.  L list: lblk = source block in H (or -1: fill)
+__global__ void __launch_bounds__(256) k_load_factor(const double* __restrict__ H, double* __restrict__ Lb, const HBlock* __restrict__ lb,
+                                                      const double* __restrict__ S, const double* __restrict__ D2, int npad, int nf) {
+  const HBlock b = lb[blockIdx.y];          // blockIdx.y = L block id
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= npad * npad) return;
+  const int i = e / npad, j = e % npad;
+  const size_t bs = (size_t)npad * npad;
+  double v = 0.0;
+  if (b.r == b.c) {
+    if (j > i) v = 0.0;
+    else if (i >= nf) v = (i == j) ? 1.0 : 0.0;
+    else {
+      v = H[(size_t)b.lblk * bs + e] * S[(size_t)b.r * npad + i] * S[(size_t)b.c * npad + j];
+      if (i == j) v += D2[(size_t)b.r * npad + i];
+    }
+  } else if (b.lblk >= 0 && i < nf && j < nf) {
+    v = H[(size_t)b.lblk * bs + e] * S[(size_t)b.r * npad + i] * S[(size_t)b.c * npad + j];
+  }
+  Lb[(size_t)blockIdx.y * bs + e] = v;
+}
+
+// out += H v over the original block structure (symmetric; diagonal blocks hold the lower triangle).
+// grid: (ceil(npad/8), H blocks), one warp per row i; also accumulates the transposed part.
+__global__ void __launch_bounds__(256) k_spmv_sym(const double* __restrict__ H, const HBlock* __restrict__ hb, const double* __restrict__ v,
+                                                   double* __restrict__ out, int npad) {
+  const HBlock b = hb[blockIdx.y];
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= npad) return;
+  const double* M = H + (size_t)blockIdx.y * npad * npad + (size_t)row * npad;
+  const double* vc = v + (size_t)b.c * npad;
+  const double vr = v[(size_t)b.r * npad + row];
+  double s = 0.0;
+  if (b.r == b.c) {
+    for (int q = lane; q <= row; q += 32) {
+      const double m = M[q];
+      s += m * vc[q];
+      if (q < row && m != 0.0) red_add(out + (size_t)b.c * npad + q, m * vr);
+    }
+  } else {
+    for (int q = lane; q < npad; q += 32) {
+      const double m = M[q];
+      s += m * vc[q];
+      if (m != 0.0 && vr != 0.0) red_add(out + (size_t)b.c * npad + q, m * vr);
+    }
+  }
+  s = warp_sum(s);
+  if (lane == 0 && s != 0.0) red_add(out + (size_t)b.r * npad + row, s);
+}
+
+}  // namespace rcvd

@@ -1,0 +1,184 @@
+"""Python binding (ctypes) of the C ABI in include/rcvd.h -- the B200 solver.
+
+`Problem` is the array-level equivalent of the reference's
+DepthVideoPoseOptimizer::poseOptimizationStep / normalizeDepth
+(lib/PoseOptimizer.cpp:890-990, :992-1147): one non-linear least-squares
+problem over per-frame [pose(6), focal, depth-transform params, spatial params].
+
+There is no CPU fallback: if librcvd_b200.so is missing or no CUDA device is
+usable, construction raises RuntimeError.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "librcvd_b200.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(the CUDA extension is mandatory, there is no CPU fallback)")
+        L = C.CDLL(path)
+        L.rcvd_last_error.restype = C.c_char_p
+        L.rcvd_launch_count.restype = C.c_int64
+        L.rcvd_problem_create.argtypes = [C.POINTER(abi.Config), C.c_int32, C.POINTER(C.c_void_p)]
+        L.rcvd_problem_destroy.argtypes = [C.c_void_p]
+        for name in ("rcvd_frame_stride", "rcvd_depth_param_offset", "rcvd_spatial_param_offset"):
+            getattr(L, name).argtypes = [C.POINTER(abi.Config)]
+        _LIB = L
+    return _LIB
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError(f"rcvd error {rc}: {lib().rcvd_last_error().decode()}")
+
+
+def frame_stride(cfg):
+    return lib().rcvd_frame_stride(C.byref(cfg))
+
+
+def depth_param_offset(cfg):
+    return lib().rcvd_depth_param_offset(C.byref(cfg))
+
+
+def spatial_param_offset(cfg):
+    return lib().rcvd_spatial_param_offset(C.byref(cfg))
+
+
+class Problem:
+    def __init__(self, cfg, device=0):
+        self.cfg = cfg
+        self.L = lib()
+        self.h = C.c_void_p()
+        _check(self.L.rcvd_problem_create(C.byref(cfg), C.c_int32(device), C.byref(self.h)))
+        self.N = cfg.num_frames
+        self.stride = frame_stride(cfg)
+        self.U = self.N * self.stride
+        self.num_constraints = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rcvd_problem_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_frames(self, in_range=None, median_depth=None, adaptive_weights=None):
+        ir = None if in_range is None else np.ascontiguousarray(in_range, np.uint8)
+        md = None if median_depth is None else np.ascontiguousarray(median_depth, np.float64)
+        aw = None if adaptive_weights is None else np.ascontiguousarray(adaptive_weights, np.float64)
+        _check(self.L.rcvd_problem_set_frames(self.h, _p(ir, C.c_uint8), _p(md, C.c_double), _p(aw, C.c_double)))
+
+    def set_constraints(self, pair_frames, offsets, records):
+        pf = np.ascontiguousarray(pair_frames, np.int32).reshape(-1, 2)
+        off = np.ascontiguousarray(offsets, np.int64)
+        rec = np.ascontiguousarray(records, np.float32).reshape(-1, 6)
+        assert off.shape[0] == pf.shape[0] + 1 and off[-1] == rec.shape[0]
+        self.num_constraints = int(rec.shape[0])
+        _check(self.L.rcvd_problem_set_constraints(self.h, C.c_int32(pf.shape[0]), _p(pf, C.c_int32), _p(off, C.c_int64), _p(rec, C.c_float)))
+
+    def set_structure(self, pair_frames):
+        pf = np.ascontiguousarray(pair_frames, np.int32).reshape(-1, 2)
+        _check(self.L.rcvd_problem_set_structure(self.h, C.c_int32(pf.shape[0]), _p(pf, C.c_int32)))
+
+    def init_comm(self, nranks, rank, unique_id):
+        uid = np.ascontiguousarray(unique_id, np.uint8)
+        assert uid.size == 128
+        _check(self.L.rcvd_problem_init_comm(self.h, C.c_int32(nranks), C.c_int32(rank), _p(uid, C.c_uint8)))
+
+    def set_state(self, x):
+        x = np.ascontiguousarray(x, np.float64).reshape(-1)
+        assert x.size == self.U
+        _check(self.L.rcvd_problem_set_state(self.h, _p(x, C.c_double)))
+
+    def get_state(self):
+        x = np.empty(self.U, np.float64)
+        _check(self.L.rcvd_problem_get_state(self.h, _p(x, C.c_double)))
+        return x.reshape(self.N, self.stride)
+
+    def evaluate(self, gradient=False):
+        cost = C.c_double()
+        g = np.zeros(self.U, np.float64) if gradient else None
+        _check(self.L.rcvd_evaluate(self.h, C.byref(cost), _p(g, C.c_double)))
+        return (cost.value, g) if gradient else cost.value
+
+    def normal_matrix_dense(self):
+        H = np.zeros((self.U, self.U), np.float64)
+        _check(self.L.rcvd_normal_matrix_dense(self.h, _p(H, C.c_double)))
+        return H
+
+    def debug_linear_solve(self, S, D2, b):
+        S = np.ascontiguousarray(S, np.float64); D2 = np.ascontiguousarray(D2, np.float64)
+        b = np.ascontiguousarray(b, np.float64); y = np.zeros_like(b)
+        _check(self.L.rcvd_debug_linear_solve(self.h, _p(S, C.c_double), _p(D2, C.c_double), _p(b, C.c_double), _p(y, C.c_double)))
+        return y
+
+    def solve(self, options=None):
+        opt = options or abi.default_solve_options()
+        s = abi.SolveSummary()
+        _check(self.L.rcvd_solve(self.h, C.byref(opt), C.byref(s)))
+        return s
+
+    def time_accumulate(self, iters=10):
+        ms = C.c_double()
+        _check(self.L.rcvd_time_accumulate(self.h, C.c_int32(iters), C.byref(ms)))
+        return ms.value
+
+    def time_iteration(self, iters=5, radius=1e4):
+        a, b, c, d = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+        _check(self.L.rcvd_time_iteration(self.h, C.c_int32(iters), C.c_double(radius), C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return {"iter_ms": a.value, "accumulate_ms": b.value, "linear_ms": c.value, "cost_ms": d.value}
+
+    def structure_info(self):
+        out = (C.c_int32 * 8)()
+        _check(self.L.rcvd_structure_info(self.h, out))
+        keys = ["frames", "offdiag_factor_blocks", "levels", "h_blocks", "npad", "stride", "tiles", "update_tasks"]
+        return dict(zip(keys, list(out)))
+
+    def launch_count(self):
+        return int(self.L.rcvd_launch_count(self.h))
+
+
+def nccl_unique_id():
+    out = np.zeros(128, np.uint8)
+    _check(lib().rcvd_nccl_unique_id(_p(out, C.c_uint8)))
+    return out
+
+
+def depth_apply(cfg, depth_params, src, device=0):
+    """DepthXform::apply (reference lib/DepthMapTransform.cpp:394-415) on the GPU."""
+    src = np.ascontiguousarray(src, np.float32); h, w = src.shape
+    dp = np.ascontiguousarray(depth_params, np.float64); dst = np.empty_like(src)
+    _check(lib().rcvd_depth_apply(C.byref(cfg), C.c_int32(device), _p(dp, C.c_double), _p(src, C.c_float), _p(dst, C.c_float), C.c_int32(h), C.c_int32(w)))
+    return dst
+
+
+def depth_param_map(cfg, depth_params, h, w, device=0):
+    """GridDepthXform::paramMap (reference lib/DepthMapTransform.cpp:950-994) on the GPU."""
+    k = 2 if cfg.value_xform == abi.VALUE_SCALESHIFT else 1
+    dp = np.ascontiguousarray(depth_params, np.float64); out = np.empty((h, w, k), np.float64)
+    _check(lib().rcvd_depth_param_map(C.byref(cfg), C.c_int32(device), _p(dp, C.c_double), _p(out, C.c_double), C.c_int32(h), C.c_int32(w)))
+    return out[:, :, 0] if k == 1 else out
+
+
+def spatial_warp(cfg, spatial_params, h, w, device=0):
+    """SpatialXform::warp (reference lib/DepthMapTransform.cpp:428-449) on the GPU."""
+    sp = np.ascontiguousarray(spatial_params, np.float64); out = np.empty((h, w, 2), np.float32)
+    _check(lib().rcvd_spatial_warp(C.byref(cfg), C.c_int32(device), _p(sp, C.c_double), _p(out, C.c_float), C.c_int32(h), C.c_int32(w)))
+    return out

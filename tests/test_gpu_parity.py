@@ -1,0 +1,94 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+Run on the B200 box with `pytest -m gpu`."""
+import numpy as np
+import pytest
+
+from robust_cvd_b200 import abi
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def _both(overrides, num_frames=8, **kw):
+    from oracle import oracle
+    from robust_cvd_b200 import solver
+    sc, cfg, pairs, offs, rec, med = helpers.make_case(num_frames=num_frames, **overrides, **kw)
+    off_d, nd = helpers.layout_numbers(cfg)
+    O = oracle.OracleProblem(cfg)
+    G = solver.Problem(cfg)
+    assert O.stride == G.stride
+    x = helpers.initial_state(sc, cfg, G.stride, off_d, nd)
+    helpers.setup_problem(O, cfg, pairs, offs, rec, med, x)
+    helpers.setup_problem(G, cfg, pairs, offs, rec, med, x)
+    return sc, cfg, O, G, x
+
+
+@pytest.mark.parametrize("name,overrides", helpers.VARIANTS, ids=[v[0] for v in helpers.VARIANTS])
+def test_cost_gradient_normal_matrix(name, overrides):
+    sc, cfg, O, G, x = _both(overrides)
+    co, go = O.evaluate(True)
+    cg, gg = G.evaluate(True)
+    assert abs(co - cg) <= 1e-11 * abs(co), (co, cg)
+    assert np.abs(go - gg).max() <= 1e-9 * max(1.0, np.abs(go).max())
+    Ho = O.normal_matrix_dense()
+    Hg = G.normal_matrix_dense()
+    assert np.abs(Ho - Hg).max() <= 1e-9 * np.abs(Ho).max()
+
+
+@pytest.mark.parametrize("name,overrides", helpers.VARIANTS[:4], ids=[v[0] for v in helpers.VARIANTS[:4]])
+def test_linear_solve(name, overrides):
+    sc, cfg, O, G, x = _both(overrides)
+    Ho = O.normal_matrix_dense()
+    U = Ho.shape[0]
+    rng = np.random.default_rng(3)
+    S = 1.0 / (1.0 + np.sqrt(np.diag(Ho)))
+    D2 = np.clip(S * S * np.diag(Ho), 1e-6, 1e32) / 1e4
+    b = rng.normal(size=U)
+    A = Ho * S[:, None] * S[None, :] + np.diag(D2)
+    y_ref = np.linalg.solve(A, b)
+    y = G.debug_linear_solve(S, D2, b)
+    res = np.linalg.norm(A @ y - b) / np.linalg.norm(b)
+    assert res < 1e-8, res
+    assert np.linalg.norm(y - y_ref) / np.linalg.norm(y_ref) < 1e-6
+
+
+@pytest.mark.parametrize("name,overrides", helpers.VARIANTS, ids=[v[0] for v in helpers.VARIANTS])
+def test_lm_solve_matches_oracle(name, overrides):
+    sc, cfg, O, G, x = _both(overrides)
+    opt = abi.default_solve_options(max_iterations=60)
+    so = O.solve(opt)
+    sg = G.solve(opt)
+    assert sg.gpu_launches > 0
+    assert so.termination == sg.termination, (so.message, sg.message)
+    assert abs(so.final_cost - sg.final_cost) <= 1e-6 * abs(so.final_cost), (so.final_cost, sg.final_cost)
+    assert abs(so.iterations - sg.iterations) <= 2
+    xo, xg = O.get_state(), G.get_state()
+    # same trajectory up to round-off: parameters agree well inside the 1e-4 relative target
+    rel = np.linalg.norm(xo - xg) / np.linalg.norm(xo)
+    assert rel < 1e-4, rel
+
+
+def test_normalize_depth_bounded():
+    """normalizeDepth problem (lib/PoseOptimizer.cpp:992-1147): scale regulariser only, lower bound 0,
+    Armijo line search along the projected path."""
+    from oracle import oracle
+    from robust_cvd_b200 import solver
+    sc, cfg, pairs, offs, rec, med = helpers.make_case(depth_type=abi.DEPTH_GLOBAL, depth_lower_bound=1, depth_deform_reg=1.0, focal_reg=0.0)
+    res = []
+    for cls in (oracle.OracleProblem, solver.Problem):
+        P = cls(cfg)
+        P.set_frames(np.ones(8, np.uint8), med)
+        P.set_constraints(np.zeros((0, 2), np.int32), np.zeros(1, np.int64), np.zeros((0, 6), np.float32))
+        P.set_state(sc.identity_state(P.stride, 7, 1))
+        s = P.solve(abi.default_solve_options())
+        res.append((s.termination, s.iterations, s.final_cost, P.get_state()[:, 7].copy()))
+    assert res[0][0] == res[1][0]
+    assert abs(res[0][1] - res[1][1]) <= 1
+    np.testing.assert_allclose(res[1][3], res[0][3], rtol=1e-6)
+    np.testing.assert_allclose(res[1][3], 1.0 / med, rtol=1e-5)
+
+
+def test_no_cpu_fallback_symbol():
+    from robust_cvd_b200 import solver
+    L = solver.lib()
+    assert L.rcvd_abi_version() == 1
