@@ -826,6 +826,16 @@ static double evaluate(Problem& P, bool wantG, bool wantH, double* costStatic = 
     int gf[3] = {f0, f1, 0}; const int ngf = (c.intr_opt == RCVD_INTR_SHARED) ? 3 : 2;
     if (wantG) gl.assign(size_t(3) * n, 0.0);
     double J[3 * kMaxP]; int cols[kMaxP]; double r[3];
+    double* tbl[3][3] = {{nullptr}}; bool tblRowIsA[3][3] = {{false}};
+    if (wantH) {
+      const int fr3[3] = {f0, f1, 0};
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) {
+        if (!(c.intr_opt == RCVD_INTR_SHARED) && (a == 2 || b == 2)) continue;
+        auto it = P.H.find({std::max(fr3[a], fr3[b]), std::min(fr3[a], fr3[b])});
+        if (it == P.H.end()) continue;
+        tbl[a][b] = it->second.data(); tblRowIsA[a][b] = fr3[a] > fr3[b];
+      }
+    }
     for (int64_t ci = beg; ci < end; ++ci) {
       const int Pn = evalStatic(P, f0, f1, &P.records[size_t(ci) * 6], P.jacMode, needJ, r, J, cols);
       const double s = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
@@ -842,19 +852,22 @@ static double evaluate(Problem& P, bool wantG, bool wantH, double* costStatic = 
         }
       }
       if (wantH) {
+        // block pointer table for the (<= 3) frames of this residual block
+        int slot[kMaxP];
+        for (int a = 0; a < Pn; ++a) { const int fr = cols[a] / n; slot[a] = (fr == f0) ? 0 : (fr == f1 ? 1 : 2); }
         for (int a = 0; a < Pn; ++a) {
           const double ja0 = J[a], ja1 = J[kMaxP + a], ja2 = J[2 * kMaxP + a];
           if (ja0 == 0.0 && ja1 == 0.0 && ja2 == 0.0) continue;
-          const int fa = cols[a] / n, la = cols[a] % n;
+          const int sa = slot[a], la = cols[a] % n;
           for (int b = 0; b <= a; ++b) {
             const double v = ja0 * J[b] + ja1 * J[kMaxP + b] + ja2 * J[2 * kMaxP + b];
             if (v == 0.0) continue;
-            const int fb = cols[b] / n, lb = cols[b] % n;
-            if (fa == fb) {
-              double* B = P.H.find({fa, fa})->second.data();
+            const int sb = slot[b], lb = cols[b] % n;
+            if (sa == sb) {
+              double* B = tbl[sa][sa];
               B[size_t(la) * n + lb] += v; if (la != lb) B[size_t(lb) * n + la] += v;
-            } else if (fa > fb) P.H.find({fa, fb})->second[size_t(la) * n + lb] += v;
-            else P.H.find({fb, fa})->second[size_t(lb) * n + la] += v;
+            } else if (tblRowIsA[sa][sb]) tbl[sa][sb][size_t(la) * n + lb] += v;
+            else tbl[sa][sb][size_t(lb) * n + la] += v;
           }
         }
       }
