@@ -111,7 +111,7 @@ def cpu_baseline_sample(wl, seconds_budget=20.0, frames=None):
     """Times one LM iteration of the CPU restatement (oracle 'port', analytic Jacobian + block Cholesky,
     all host threads) on a bounded sample (a prefix of the frames) of the same workload."""
     from oracle import oracle
-    nthreads = os.cpu_count() or 1
+    nthreads = oracle.effective_cpus()
     oracle.set_threads(nthreads)
     nf = frames or 48
     spec, sc, cfg, pairs, offs, rec, med = build_case(wl, frames=nf)

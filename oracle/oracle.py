@@ -31,6 +31,7 @@ def lib():
         L.orc_problem_destroy.argtypes = [C.c_void_p]
         L.orc_frame_stride.argtypes = [C.POINTER(abi.Config)]
         _LIB = L
+        L.orc_set_threads(C.c_int32(effective_cpus()))
     return _LIB
 
 
@@ -147,6 +148,30 @@ def gather_spatial(cfg, lx, ly):
     idx = np.zeros(16, np.int32); w = np.zeros(16, np.float64)
     n = lib().orc_gather_spatial(C.byref(cfg), C.c_float(lx), C.c_float(ly), _p(idx, C.c_int32), _p(w, C.c_double))
     return idx[:n].copy(), w[:n].copy()
+
+
+def effective_cpus():
+    """CPUs this container may actually use: min(visible CPUs, cgroup quota)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, q // per))
+            break
+        except Exception:
+            continue
+    return n
 
 
 def set_threads(n):

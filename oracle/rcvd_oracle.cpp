@@ -985,10 +985,9 @@ struct BlockChol {
     }
     return true;
   }
-  // X <- X * Lkk^{-T}: each row x solves x Lkk^T = a
-  static void trsm(double* X, const double* Lkk, int n) {
-#pragma omp parallel for schedule(static)
-    for (int i = 0; i < n; ++i) {
+  // X <- X * Lkk^{-T} for rows [r0, r1): each row x solves x Lkk^T = a  (serial; parallelism is over strips)
+  static void trsmRows(double* X, const double* Lkk, int n, int r0, int r1) {
+    for (int i = r0; i < r1; ++i) {
       double* x = X + size_t(i) * n;
       for (int j = 0; j < n; ++j) {
         const double* Lj = Lkk + size_t(j) * n;
@@ -999,11 +998,10 @@ struct BlockChol {
       }
     }
   }
-  // C -= A * B^T  (all n x n row-major), 4x4 register tiles of dot products
-  static void gemmNT(double* C, const double* A, const double* B, int n) {
-#pragma omp parallel for schedule(static) collapse(2)
-    for (int i0 = 0; i0 < n; i0 += 4) for (int j0 = 0; j0 < n; j0 += 4) {
-      const int im = std::min(4, n - i0), jm = std::min(4, n - j0);
+  // C[r0:r1, :] -= A[r0:r1, :] * B^T  (n x n row-major), 4x4 register tiles of dot products, serial
+  static void gemmNTRows(double* C, const double* A, const double* B, int n, int r0, int r1) {
+    for (int i0 = r0; i0 < r1; i0 += 4) for (int j0 = 0; j0 < n; j0 += 4) {
+      const int im = std::min(4, r1 - i0), jm = std::min(4, n - j0);
       double acc[4][4] = {{0}};
       if (im == 4 && jm == 4) {
         const double *a0 = A + size_t(i0) * n, *a1 = a0 + n, *a2 = a1 + n, *a3 = a2 + n;
@@ -1019,23 +1017,47 @@ struct BlockChol {
         acc[0][0] = c00; acc[0][1] = c01; acc[0][2] = c02; acc[0][3] = c03; acc[1][0] = c10; acc[1][1] = c11; acc[1][2] = c12; acc[1][3] = c13;
         acc[2][0] = c20; acc[2][1] = c21; acc[2][2] = c22; acc[2][3] = c23; acc[3][0] = c30; acc[3][1] = c31; acc[3][2] = c32; acc[3][3] = c33;
       } else {
-        for (int i = 0; i < im; ++i) for (int j = 0; j < jm; ++j) { double s = 0; for (int p = 0; p < n; ++p) s += A[size_t(i0 + i) * n + p] * B[size_t(j0 + j) * n + p]; acc[i][j] = s; }
+        for (int i = 0; i < im; ++i) for (int j = 0; j < jm; ++j) { double sacc = 0; for (int p = 0; p < n; ++p) sacc += A[size_t(i0 + i) * n + p] * B[size_t(j0 + j) * n + p]; acc[i][j] = sacc; }
       }
       for (int i = 0; i < im; ++i) for (int j = 0; j < jm; ++j) C[size_t(i0 + i) * n + j0 + j] -= acc[i][j];
     }
   }
+  // Level-scheduled right-looking factorisation; OpenMP over (block task x 16-row strip) work items.
   bool factor() {
-    for (int k : order) {
-      double* Lkk = L[{k, k}].data();
-      if (!potrf(Lkk, n)) return false;
-      const auto& st = cstruct[k];
-      for (int r : st) trsm(L[{r, k}].data(), Lkk, n);
-      for (size_t a = 0; a < st.size(); ++a) for (size_t b = 0; b <= a; ++b) {
-        const int r = st[a], c = st[b];  // pos[r] >= pos[c]
-        gemmNT(L[{r, c}].data(), L[{r, k}].data(), L[{c, k}].data(), n);
+    std::vector<int> lvl(N, 0); int nl = 0;
+    for (int k : order) { for (int a : cstruct[k]) lvl[a] = std::max(lvl[a], lvl[k] + 1); nl = std::max(nl, lvl[k] + 1); }
+    std::vector<std::vector<int>> lf(nl);
+    for (int k : order) lf[lvl[k]].push_back(k);
+    const int strip = 16, ns = (n + strip - 1) / strip;
+    bool ok = true;
+    for (int l = 0; l < nl && ok; ++l) {
+      const std::vector<int>& fr = lf[l];
+      std::vector<char> good(fr.size(), 1);
+#pragma omp parallel for schedule(dynamic, 1)
+      for (size_t q = 0; q < fr.size(); ++q) good[q] = potrf(L[{fr[q], fr[q]}].data(), n) ? 1 : 0;
+      for (char gch : good) if (!gch) ok = false;
+      if (!ok) break;
+      struct TItem { double* X; const double* Lkk; };
+      std::vector<TItem> titems;
+      for (int k : fr) for (int r : cstruct[k]) titems.push_back({L[{r, k}].data(), L[{k, k}].data()});
+      const long nt = (long)titems.size() * ns;
+#pragma omp parallel for schedule(dynamic, 1)
+      for (long w = 0; w < nt; ++w) { const TItem& t = titems[w / ns]; const int r0 = int(w % ns) * strip; trsmRows(t.X, t.Lkk, n, r0, std::min(n, r0 + strip)); }
+      // updates grouped by target block so that no two work items write the same rows
+      std::map<std::pair<int, int>, std::vector<std::pair<const double*, const double*>>> upd;
+      for (int k : fr) { const auto& st = cstruct[k];
+        for (size_t a = 0; a < st.size(); ++a) for (size_t b = 0; b <= a; ++b) upd[{st[a], st[b]}].push_back({L[{st[a], k}].data(), L[{st[b], k}].data()}); }
+      struct UItem { double* C; const std::vector<std::pair<const double*, const double*>>* src; };
+      std::vector<UItem> uitems;
+      for (auto& kv : upd) uitems.push_back({L[kv.first].data(), &kv.second});
+      const long nu = (long)uitems.size() * ns;
+#pragma omp parallel for schedule(dynamic, 1)
+      for (long w = 0; w < nu; ++w) {
+        const UItem& u = uitems[w / ns]; const int r0 = int(w % ns) * strip, r1 = std::min(n, r0 + strip);
+        for (auto& pr : *u.src) gemmNTRows(u.C, pr.first, pr.second, n, r0, r1);
       }
     }
-    return true;
+    return ok;
   }
   void solve(double* b) const {  // in place, b indexed by frame*n
     std::vector<double> tmp(n);

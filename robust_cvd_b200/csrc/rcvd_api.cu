@@ -387,7 +387,8 @@ static int build_structure(rcvd_problem* p) {
   const int dyn = npad * 17 * (int)sizeof(double);
   if (dyn > 200 * 1024) return set_err(RCVD_ERR_INVALID, "frame block too large for the single-CTA factor kernel (npad=%d)", npad);
   CK(cudaFuncSetAttribute(k_potrf, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-  CK(cudaFuncSetAttribute(k_trinv, cudaFuncAttributeMaxDynamicSharedMemorySize, npad * 16 * (int)sizeof(double)));
+  CK(cudaFuncSetAttribute(k_trinv, cudaFuncAttributeMaxDynamicSharedMemorySize, (npad * 16 + 16 * (npad + 1)) * (int)sizeof(double)));
+  if (potrf_smem_bytes(npad) <= 200 * 1024) CK(cudaFuncSetAttribute(k_potrf_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_smem_bytes(npad)));
   CK(cudaStreamSynchronize(p->stream));
   p->structure_ready = true;
   return RCVD_OK;
@@ -401,8 +402,11 @@ static int enqueue_factor_solve(rcvd_problem* p) {
   k_load_factor<<<dim3((npad * npad + 255) / 256, nL), 256, 0, st>>>(p->d_H, p->d_Lb, p->d_lblocks, p->d_S, p->d_D2, npad, L.nf);
   p->launches += 1;
   for (const Level& lv : p->levels) {
-    k_potrf<<<lv.nframes, kPotrfThreads, npad * 17 * sizeof(double), st>>>(p->d_Lb, p->d_invT, p->d_lvl_frames + lv.frame_off, npad, p->d_fail);
-    k_trinv<<<dim3(npad / 16, lv.nframes), 256, npad * 16 * sizeof(double), st>>>(p->d_Lb, p->d_invT, p->d_invL, p->d_lvl_frames + lv.frame_off, npad);
+    if (potrf_smem_bytes(npad) <= 200 * 1024)
+      k_potrf_smem<<<lv.nframes, kPotrfSmemThreads, potrf_smem_bytes(npad), st>>>(p->d_Lb, p->d_invT, p->d_lvl_frames + lv.frame_off, npad, p->d_fail);
+    else
+      k_potrf<<<lv.nframes, kPotrfThreads, npad * 17 * sizeof(double), st>>>(p->d_Lb, p->d_invT, p->d_lvl_frames + lv.frame_off, npad, p->d_fail);
+    k_trinv<<<dim3(npad / 16, lv.nframes), 256, (npad * 16 + 16 * (npad + 1)) * sizeof(double), st>>>(p->d_Lb, p->d_invT, p->d_invL, p->d_lvl_frames + lv.frame_off, npad);
     p->launches += 2;
     if (lv.ntrsm > 0) { k_gemm_nt<<<dim3(tiles, tiles, lv.ntrsm), 128, 0, st>>>(p->d_T, p->d_Lb, p->d_invL, p->d_trsm_tasks + lv.trsm_off, p->d_trsm_pairs, npad, 1.0, 0.0); p->launches++; }
     if (lv.nupd > 0) { k_gemm_nt<<<dim3(tiles, tiles, lv.nupd), 128, 0, st>>>(p->d_Lb, p->d_T, p->d_T, p->d_upd_tasks + lv.upd_off, p->d_upd_pairs, npad, -1.0, 1.0); p->launches++; }
@@ -415,9 +419,9 @@ static int enqueue_factor_solve(rcvd_problem* p) {
   }
   for (int l = (int)p->levels.size() - 1; l >= 0; --l) {
     const Level& lv = p->levels[l];
-    k_bwd_update<<<dim3((npad + 255) / 256, lv.nframes), 256, 0, st>>>(p->d_T, p->d_y, p->d_ytmp, p->d_lvl_frames + lv.frame_off, p->d_col_ptr, p->d_col_tasks, npad);
-    k_bwd_diag<<<dim3((npad + 255) / 256, lv.nframes), 256, 0, st>>>(p->d_invL, p->d_ytmp, p->d_y, p->d_lvl_frames + lv.frame_off, npad);
-    p->launches += 2;
+    if (lv.nfwd > 0) { k_bwd_update<<<dim3((npad + 31) / 32, lv.nfwd), 256, 0, st>>>(p->d_T, p->d_y, p->d_ytmp, p->d_fwd_tasks + lv.fwd_off, npad); p->launches++; }
+    k_bwd_diag<<<dim3((npad + 31) / 32, lv.nframes), 256, 0, st>>>(p->d_invL, p->d_ytmp, p->d_y, p->d_lvl_frames + lv.frame_off, npad);
+    p->launches += 1;
   }
   CK(cudaGetLastError());
   return RCVD_OK;

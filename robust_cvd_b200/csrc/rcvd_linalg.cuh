@@ -124,16 +124,144 @@ __global__ void __launch_bounds__(kPotrfThreads) k_potrf(double* __restrict__ Lb
 }
 
 // ---------------------------------------------------------------------------
+// k_potrf_smem: same factorisation with the whole lower triangle resident in shared memory
+// (npad <= 208: 91 tiles x 16 x 17 doubles = 198 KB of the 227 KB a CTA may use).
+// ---------------------------------------------------------------------------
+constexpr int kPotrfSmemThreads = 512;
+constexpr int kTileLd = 17, kTileSz = 16 * kTileLd;
+__host__ __device__ inline size_t potrf_smem_bytes(int npad) { const int nt = npad / 16; return (size_t)(nt * (nt + 1) / 2) * kTileSz * sizeof(double); }
+
+__global__ void __launch_bounds__(kPotrfSmemThreads) k_potrf_smem(double* __restrict__ Lb, double* __restrict__ invT,
+                                                                   const int* __restrict__ frames, int npad, int* __restrict__ fail) {
+  extern __shared__ double tiles[];
+  __shared__ double Di[16][17];
+  const int frame = frames[blockIdx.x];
+  double* A = Lb + (size_t)frame * npad * npad;
+  double* iT = invT + (size_t)frame * npad * 16;
+  const int nt = npad / 16, ntl = nt * (nt + 1) / 2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = kPotrfSmemThreads / 32;
+  // load the lower tiles (one 16x16 tile per 256 consecutive work items; rows are 128 B segments)
+  for (int idx = tid; idx < ntl * 256; idx += kPotrfSmemThreads) {
+    const int t = idx >> 8, e = idx & 255, r = e >> 4, c = e & 15;
+    int ti = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    while (ti * (ti + 1) / 2 > t) --ti;
+    const int tj = t - ti * (ti + 1) / 2;
+    tiles[(size_t)t * kTileSz + r * kTileLd + c] = A[(size_t)(ti * 16 + r) * npad + tj * 16 + c];
+  }
+  __syncthreads();
+  for (int jb = 0; jb < nt; ++jb) {
+    double* D = tiles + (size_t)(jb * (jb + 1) / 2 + jb) * kTileSz;
+    if (warp == 0) {
+      // register-resident right-looking Cholesky of the 16x16 tile: lane i (< 16) owns row i
+      const int i = lane & 15;
+      double a[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) a[c] = (c <= i) ? D[i * kTileLd + c] : 0.0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        double d = __shfl_sync(0xffffffffu, a[j], j);        // pivot a_jj (already updated)
+        if (!(d > 0.0) || !isfinite(d)) { if (lane == 0) *fail = 1; d = 1.0; }
+        const double pinv = rsqrt(d);
+        const double lij = (i == j) ? d * pinv : a[j] * pinv;   // l_jj = sqrt(d), l_ij = a_ij / sqrt(d)
+        if (i >= j) a[j] = lij;
+#pragma unroll
+        for (int c = j + 1; c < 16; ++c) {
+          const double lcj = __shfl_sync(0xffffffffu, a[j], c);  // l_cj (lane c has just stored it)
+          if (i >= c) a[c] -= lij * lcj;
+        }
+      }
+      // inverse of the triangular tile, lane c = column c: forward substitution with rows broadcast by shuffle
+      {
+        const int cidx = lane & 15;
+        double xcol[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          double sacc = (r == cidx) ? 1.0 : 0.0;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            if (q < r) { const double lrq = __shfl_sync(0xffffffffu, a[q], r); sacc -= lrq * xcol[q]; }
+          }
+          const double lrr = __shfl_sync(0xffffffffu, a[r], r);
+          xcol[r] = (r < cidx) ? 0.0 : sacc / lrr;
+        }
+        if (lane < 16) {
+#pragma unroll
+          for (int r = 0; r < 16; ++r) { Di[r][cidx] = xcol[r]; iT[(size_t)jb * 256 + r * 16 + cidx] = xcol[r]; }
+#pragma unroll
+          for (int c = 0; c < 16; ++c) D[i * kTileLd + c] = a[c];
+        }
+      }
+    }
+    __syncthreads();
+    // panel: tile(ti, jb) <- tile(ti, jb) * Di^T
+    for (int ti = jb + 1 + warp; ti < nt; ti += nw) {
+      double* Tt = tiles + (size_t)(ti * (ti + 1) / 2 + jb) * kTileSz;
+      const int r = lane >> 1, c0 = (lane & 1) * 8;
+      double a[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) a[q] = Tt[r * kTileLd + q];
+      __syncwarp();
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) {
+        const int c = c0 + cc;
+        double sacc = 0.0;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) if (q <= c) sacc += a[q] * Di[c][q];
+        Tt[r * kTileLd + c] = sacc;
+      }
+    }
+    __syncthreads();
+    // trailing update: tile(ti, tj) -= X_ti X_tj^T, jb < tj <= ti
+    const int m = nt - jb - 1, ntr = m * (m + 1) / 2;
+    for (int tl = warp; tl < ntr; tl += nw) {
+      int ti = (int)((sqrtf(8.f * tl + 1.f) - 1.f) * 0.5f);
+      while ((ti + 1) * (ti + 2) / 2 <= tl) ++ti;
+      while (ti * (ti + 1) / 2 > tl) --ti;
+      const int tj = tl - ti * (ti + 1) / 2;
+      const int gi = jb + 1 + ti, gj = jb + 1 + tj;
+      const double* Xi = tiles + (size_t)(gi * (gi + 1) / 2 + jb) * kTileSz;
+      const double* Xj = tiles + (size_t)(gj * (gj + 1) / 2 + jb) * kTileSz;
+      double* Ct = tiles + (size_t)(gi * (gi + 1) / 2 + gj) * kTileSz;
+      const int r = lane >> 1, c0 = (lane & 1) * 8;
+      double acc[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const double av = Xi[r * kTileLd + q];
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) acc[cc] += av * Xj[(c0 + cc) * kTileLd + q];
+      }
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) Ct[r * kTileLd + c0 + cc] -= acc[cc];
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < ntl * 256; idx += kPotrfSmemThreads) {
+    const int t = idx >> 8, e = idx & 255, r = e >> 4, c = e & 15;
+    int ti = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    while (ti * (ti + 1) / 2 > t) --ti;
+    const int tj = t - ti * (ti + 1) / 2;
+    const double v = tiles[(size_t)t * kTileSz + r * kTileLd + c];
+    A[(size_t)(ti * 16 + r) * npad + tj * 16 + c] = (ti == tj && c > r) ? 0.0 : v;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // k_trinv: inv(L_kk), one CTA per 16-column panel j; forward substitution by tiles using the
 // diagonal-tile inverses from k_potrf.  Writes the full npad x npad block (zeros above).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_trinv(const double* __restrict__ Lb, const double* __restrict__ invT, double* __restrict__ invL,
                                                 const int* __restrict__ frames, int npad) {
-  extern __shared__ double Z[];   // [nt][16][16] tile column j of the inverse (only tiles >= j used)
+  extern __shared__ double Z[];   // [nt][16][16] tile column j of the inverse (tiles >= j), then the staged L row panel [16][npad+1]
   __shared__ double W[16][17];
   const int frame = frames[blockIdx.y];
   const int j = blockIdx.x;
   const int nt = npad / 16;
+  double* Lrow_s = Z + (size_t)nt * 256;
+  const int ldp = npad + 1;
   const double* A = Lb + (size_t)frame * npad * npad;
   const double* iT = invT + (size_t)frame * npad * 16;
   double* out = invL + (size_t)frame * npad * npad;
@@ -143,13 +271,14 @@ __global__ void __launch_bounds__(256) k_trinv(const double* __restrict__ Lb, co
   out[(size_t)(j * 16 + r) * npad + j * 16 + c] = Z[(size_t)j * 256 + tid];
   __syncthreads();
   for (int i = j + 1; i < nt; ++i) {
+    // stage L[i*16 .. i*16+15][j*16 .. i*16-1] (coalesced 128 B row segments)
+    const int kw = (i - j) * 16;
+    for (int e = tid; e < 16 * kw; e += 256) { const int rr = e / kw, kk = e % kw; Lrow_s[rr * ldp + kk] = A[(size_t)(i * 16 + rr) * npad + j * 16 + kk]; }
+    __syncthreads();
     double s = 0.0;
-    const double* Lrow = A + (size_t)(i * 16 + r) * npad;
-    for (int p = j; p < i; ++p) {
-      const double* zp = Z + (size_t)p * 256;
-#pragma unroll
-      for (int q = 0; q < 16; ++q) s += Lrow[p * 16 + q] * zp[q * 16 + c];
-    }
+    const double* lr = Lrow_s + r * ldp;
+    const double* zp = Z + (size_t)j * 256 + c;
+    for (int kk = 0; kk < kw; ++kk) s += lr[kk] * zp[(size_t)kk * 16];
     W[r][c] = s;
     __syncthreads();
     double zv = 0.0;
@@ -290,33 +419,52 @@ __global__ void __launch_bounds__(256) k_fwd_update(const double* __restrict__ T
   s = warp_sum(s);
   if (lane == 0) red_add(rhs + (size_t)tk.r * npad + row, -s);
 }
-// y_k -= sum_{r in struct(k)} T_rk^T x_r   (grid: (ceil(npad/256), frames in level)); CSR over frames
+// y_k -= T_rk^T x_r for every factor block (r,k) of the level.
+// grid: (ceil(npad/32), tasks in level); 256 threads = 32 columns x 8 row groups, coalesced row reads,
+// smem reduction over the row groups, one RED per column.
 __global__ void __launch_bounds__(256) k_bwd_update(const double* __restrict__ T, const double* __restrict__ x, double* __restrict__ y,
-                                                     const int* __restrict__ frames, const int* __restrict__ col_ptr,
-                                                     const SolveTask* __restrict__ col_tasks, int npad) {
-  const int frame = frames[blockIdx.y];
-  const int j = blockIdx.x * 256 + threadIdx.x;
-  if (j >= npad) return;
+                                                     const SolveTask* __restrict__ tasks, int npad) {
+  __shared__ double red[8][33];
+  const SolveTask tk = tasks[blockIdx.y];
+  const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + cl;
   double acc = 0.0;
-  for (int e = col_ptr[frame]; e < col_ptr[frame + 1]; ++e) {
-    const SolveTask tk = col_tasks[e];
+  if (j < npad) {
     const double* M = T + (size_t)tk.blk * npad * npad + j;
     const double* xr = x + (size_t)tk.r * npad;
-    for (int i = 0; i < npad; ++i) acc += M[(size_t)i * npad] * xr[i];
+    for (int i = rg; i < npad; i += 8) acc += M[(size_t)i * npad] * xr[i];
   }
-  y[(size_t)frame * npad + j] -= acc;
+  red[rg][cl] = acc;
+  __syncthreads();
+  if (rg == 0 && j < npad) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += red[q][cl];
+    if (s != 0.0) red_add(y + (size_t)tk.k * npad + j, -s);
+  }
 }
-// x_k = inv(L_kk)^T y_k    (grid: (ceil(npad/256), frames in level))
+// x_k = inv(L_kk)^T y_k    (grid: (ceil(npad/32), frames in level)); same thread layout
 __global__ void __launch_bounds__(256) k_bwd_diag(const double* __restrict__ invL, const double* __restrict__ y, double* __restrict__ x,
                                                    const int* __restrict__ frames, int npad) {
+  __shared__ double red[8][33];
   const int frame = frames[blockIdx.y];
-  const int j = blockIdx.x * 256 + threadIdx.x;
-  if (j >= npad) return;
-  const double* M = invL + (size_t)frame * npad * npad + j;
-  const double* v = y + (size_t)frame * npad;
+  const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + cl;
   double acc = 0.0;
-  for (int i = j; i < npad; ++i) acc += M[(size_t)i * npad] * v[i];
-  x[(size_t)frame * npad + j] = acc;
+  if (j < npad) {
+    const double* M = invL + (size_t)frame * npad * npad + j;
+    const double* v = y + (size_t)frame * npad;
+    const int i0 = j - (j % 8) + rg;            // first row >= j in this row group (rows < j are zero anyway)
+    for (int i = (i0 < j ? i0 + 8 : i0); i < npad; i += 8) acc += M[(size_t)i * npad] * v[i];
+  }
+  red[rg][cl] = acc;
+  __syncthreads();
+  if (rg == 0 && j < npad) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += red[q][cl];
+    x[(size_t)frame * npad + j] = s;
+  }
 }
 
 // ---------------------------------------------------------------------------
