@@ -25,6 +25,12 @@ using namespace rcvd;
 
 #define RCVD_API extern "C" __attribute__((visibility("default")))
 
+constexpr int kFastSmem = (3 * kTile * kJsLd + 4 * 256) * (int)sizeof(double);
+static bool fast_path_ok_host(const rcvd_config& c, const Layout& L) {
+  return L.k == 1 && c.spatial_type == RCVD_SPATIAL_IDENTITY && c.intr_opt != RCVD_INTR_SHARED && !c.fix_poses && !c.fix_depth_xforms &&
+         !c.fix_spatial_xforms && (c.depth_type != RCVD_DEPTH_GRID || !c.depth_cubic);
+}
+
 static thread_local std::string g_err = "";
 static int set_err(int code, const char* fmt, ...) {
   char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
@@ -199,7 +205,7 @@ struct rcvd_problem {
   // multi GPU
   int nranks = 1, rank = 0; nccl::Comm comm = nullptr;
   int64_t launches = 0, graph_launches = 0;
-  std::vector<double> h_state; bool state_dirty = false;
+  std::vector<double> h_state; bool state_dirty = false; bool use_fast = true;
   double *d_g2 = nullptr, *d_delta = nullptr; int* h_fail = nullptr;
   cudaEvent_t ev[8] = {nullptr};
   std::vector<void*> allocs;
@@ -305,7 +311,7 @@ static int build_structure(rcvd_problem* p) {
       lvl_frames.push_back(k);
       for (int r : cs[k]) {
         const int id = lid[{r, k}];
-        trsm_tasks.push_back({id - N, (int)trsm_pairs.size(), 1, 0});
+        trsm_tasks.push_back({id - N, (int)trsm_pairs.size(), 1, 2});
         trsm_pairs.push_back(make_int2(id, k));
         fwd_tasks.push_back({id - N, r, k});
       }
@@ -388,7 +394,8 @@ static int build_structure(rcvd_problem* p) {
   if (dyn > 200 * 1024) return set_err(RCVD_ERR_INVALID, "frame block too large for the single-CTA factor kernel (npad=%d)", npad);
   CK(cudaFuncSetAttribute(k_potrf, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
   CK(cudaFuncSetAttribute(k_trinv, cudaFuncAttributeMaxDynamicSharedMemorySize, (npad * 16 + 16 * (npad + 1)) * (int)sizeof(double)));
-  if (potrf_smem_bytes(npad) <= 200 * 1024) CK(cudaFuncSetAttribute(k_potrf_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_smem_bytes(npad)));
+  CK(cudaFuncSetAttribute(k_accumulate_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem));
+  if (potrf_smem_bytes(npad) <= 220 * 1024) CK(cudaFuncSetAttribute(k_potrf_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_smem_bytes(npad)));
   CK(cudaStreamSynchronize(p->stream));
   p->structure_ready = true;
   return RCVD_OK;
@@ -402,7 +409,7 @@ static int enqueue_factor_solve(rcvd_problem* p) {
   k_load_factor<<<dim3((npad * npad + 255) / 256, nL), 256, 0, st>>>(p->d_H, p->d_Lb, p->d_lblocks, p->d_S, p->d_D2, npad, L.nf);
   p->launches += 1;
   for (const Level& lv : p->levels) {
-    if (potrf_smem_bytes(npad) <= 200 * 1024)
+    if (potrf_smem_bytes(npad) <= 220 * 1024)
       k_potrf_smem<<<lv.nframes, kPotrfSmemThreads, potrf_smem_bytes(npad), st>>>(p->d_Lb, p->d_invT, p->d_lvl_frames + lv.frame_off, npad, p->d_fail);
     else
       k_potrf<<<lv.nframes, kPotrfThreads, npad * 17 * sizeof(double), st>>>(p->d_Lb, p->d_invT, p->d_lvl_frames + lv.frame_off, npad, p->d_fail);
@@ -450,6 +457,7 @@ static int factor_solve(rcvd_problem* p) {
 // ---------------------------------------------------------------------------
 // Evaluation
 // ---------------------------------------------------------------------------
+
 static int allreduce(rcvd_problem* p, double* buf, size_t count) {
   if (p->nranks <= 1) return RCVD_OK;
   const int r = nccl::AllReduce(buf, buf, count, nccl::kFloat64, nccl::kSum, p->comm, p->stream);
@@ -467,7 +475,8 @@ static int enqueue_evaluate(rcvd_problem* p, const double* x, bool wantG, bool w
   if (wantH) CK(cudaMemsetAsync(p->d_H, 0, (size_t)p->nHblocks * bs * sizeof(double), st));
   if (wantG) CK(cudaMemsetAsync(gout, 0, (Upad + 8) * sizeof(double), st));
   if (p->num_tiles > 0) {
-    if (wantH) k_accumulate_generic<true><<<p->num_tiles, kTile, 0, st>>>(d, x, p->d_H, gout, p->d_partial);
+    if (wantH && p->use_fast && fast_path_ok_host(p->cfg, L)) k_accumulate_fast<<<p->num_tiles, kTile, kFastSmem, st>>>(d, x, p->d_H, gout, p->d_partial);
+    else if (wantH) k_accumulate_generic<true><<<p->num_tiles, kTile, 0, st>>>(d, x, p->d_H, gout, p->d_partial);
     else if (wantG) k_accumulate_generic<false><<<p->num_tiles, kTile, 0, st>>>(d, x, nullptr, gout, p->d_partial);
     else k_cost_static<<<p->num_tiles, kTile, 0, st>>>(d, x, p->d_partial);
     p->launches++;
@@ -965,6 +974,8 @@ RCVD_API int32_t rcvd_time_iteration(rcvd_problem* p, int32_t iters, double radi
   return RCVD_OK;
 }
 RCVD_API int64_t rcvd_launch_count(rcvd_problem* p) { return p ? p->launches : 0; }
+// Test hook: 0 forces the generic accumulate kernel, 1 (default) allows the specialised one.
+RCVD_API int32_t rcvd_debug_set_fast_path(rcvd_problem* p, int32_t on) { if (!p) return RCVD_ERR_INVALID; p->use_fast = on != 0; return RCVD_OK; }
 RCVD_API int32_t rcvd_solve(rcvd_problem* p, const rcvd_solve_options* opt, rcvd_solve_summary* summary) {
   if (!p || !summary) return set_err(RCVD_ERR_INVALID, "null argument");
   CK(cudaSetDevice(p->device));

@@ -170,6 +170,179 @@ __global__ void __launch_bounds__(kTile) k_accumulate_generic(DevProblem p, cons
   block_store_sum(cost, partial + t);
 }
 
+// ---------------------------------------------------------------------------
+// K1 (fast path): depth transform Identity / Global / bilinear Grid with Scale value transform,
+// identity spatial transform, PerFrame or Fixed intrinsics, nothing held constant -- the
+// reference's default configuration (pose_optimization.py:197-207 + coarse-to-fine grids).
+// Per constraint the Jacobian is kept in "local" variables (pose 6, focal, depth D per frame:
+// 3 x 16); the dense 14 x 14 pose/focal normal block and its gradient are reduced over the
+// 128 constraints of the tile on the fp64 tensor cores (J^T [J | r] as an m8n8k4 DMMA GEMM with
+// K = 3 x 128 residual rows staged in shared memory), so they cost 119 L2 reductions per tile
+// instead of per constraint.  The spline-node columns (<= 4 nodes per frame) are expanded per
+// thread and scattered with RED.ADD.F64.
+// ---------------------------------------------------------------------------
+constexpr int kJsLd = 20;   // [k][col] staging layout, 20-double rows: conflict-free DMMA fragment loads
+
+__device__ __forceinline__ void dmma_acc(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ bool fast_path_ok(const rcvd_config& c, const Layout& L) {
+  return L.k == 1 && c.spatial_type == RCVD_SPATIAL_IDENTITY && c.intr_opt != RCVD_INTR_SHARED && !c.fix_poses && !c.fix_depth_xforms &&
+         !c.fix_spatial_xforms && (c.depth_type != RCVD_DEPTH_GRID || !c.depth_cubic);
+}
+
+__global__ void __launch_bounds__(kTile) k_accumulate_fast(DevProblem p, const double* __restrict__ x, double* __restrict__ H,
+                                                            double* __restrict__ g, double* __restrict__ partial) {
+  extern __shared__ __align__(16) double sm[];
+  double* Js = sm;                                  // [3*kTile][kJsLd]
+  double* Ms = sm + 3 * kTile * kJsLd;              // [4 warps][16][16]
+  const rcvd_config& c = p.cfg; const Layout& L = p.L;
+  const int t = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int pr = p.tile_pair[t];
+  const int f0 = p.pair_frames[2 * pr], f1 = p.pair_frames[2 * pr + 1];
+  const int np = L.npad;
+  const size_t bs = (size_t)np * np;
+  const int enc = p.blk_of[f0 * p.N + f1];          // cross block id*2 + (f0 is the row side)
+  double* Hx = H + (size_t)(enc >> 1) * bs;
+  const bool f0rows = enc & 1;
+  double* H0 = H + (size_t)f0 * bs; double* H1 = H + (size_t)f1 * bs;
+  double cost = 0.0;
+  const bool active = tid < p.tile_count[t];
+  double Jl[60]; double r0 = 0, r1 = 0, r2 = 0;
+  int nn = 0; int idx0[4], idx1[4]; double w0[4], w1[4];
+#pragma unroll
+  for (int i = 0; i < 60; ++i) Jl[i] = 0.0;
+  if (active) {
+    const float* rec = p.records + (size_t)(p.tile_begin[t] + tid) * 6;
+    const double* pf0 = x + (size_t)f0 * L.nf; const double* pf1 = x + (size_t)f1 * L.nf;
+    ObsIn o0{rec[0], rec[1], rec[2]}, o1{rec[3], rec[4], rec[5]};
+    double D0 = (double)o0.depth, D1 = (double)o1.depth;
+    if (c.depth_type == RCVD_DEPTH_GLOBAL) {
+      nn = 1; idx0[0] = 0; idx1[0] = 0; w0[0] = D0; w1[0] = D1;          // dD/ds = src
+      D0 *= pf0[L.offD]; D1 *= pf1[L.offD];
+    } else if (c.depth_type == RCVD_DEPTH_GRID) {
+      nn = 4;
+      int ix, iy; double rx, ry;
+      cell_coord(o0.ndcx, c.depth_grid_x, ix, rx); cell_coord(o0.ndcy, c.depth_grid_y, iy, ry);
+      idx0[0] = ix + iy * c.depth_grid_x; idx0[1] = idx0[0] + 1; idx0[2] = idx0[0] + c.depth_grid_x; idx0[3] = idx0[2] + 1;
+      double ox = __dsub_rn(1.0, rx), oy = __dsub_rn(1.0, ry);
+      w0[0] = __dmul_rn(ox, oy); w0[1] = __dmul_rn(rx, oy); w0[2] = __dmul_rn(ox, ry); w0[3] = __dmul_rn(rx, ry);
+      cell_coord(o1.ndcx, c.depth_grid_x, ix, rx); cell_coord(o1.ndcy, c.depth_grid_y, iy, ry);
+      idx1[0] = ix + iy * c.depth_grid_x; idx1[1] = idx1[0] + 1; idx1[2] = idx1[0] + c.depth_grid_x; idx1[3] = idx1[2] + 1;
+      ox = __dsub_rn(1.0, rx); oy = __dsub_rn(1.0, ry);
+      w1[0] = __dmul_rn(ox, oy); w1[1] = __dmul_rn(rx, oy); w1[2] = __dmul_rn(ox, ry); w1[3] = __dmul_rn(rx, ry);
+      // GridDepthFunctor::eval: res += (src * s_i) * w_i, in node order
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { a0 += (D0 * pf0[L.offD + idx0[q]]) * w0[q]; a1 += (D1 * pf1[L.offD + idx1[q]]) * w1[q]; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { w0[q] *= D0; w1[q] *= D1; }          // dD/ds_i = w_i * src
+      D0 = a0; D1 = a1;
+    }
+    const double phi0 = (c.intr_opt == RCVD_INTR_PER_FRAME) ? pf0[6] : c.fixed_vfocal;
+    const double phi1 = (c.intr_opt == RCVD_INTR_PER_FRAME) ? pf1[6] : c.fixed_vfocal;
+    const double u[2] = {0.0, 0.0};
+    double r[3];
+    static_scene<true>(c, pf0, phi0, D0, u, pf1, phi1, D1, u, o0, o1, r, Jl);
+    const double s = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    double rho0, rho1;
+    robust_loss(c, s, rho0, rho1);
+    cost = 0.5 * rho0;
+    const double sc = sqrt(rho1);
+    r0 = r[0] * sc; r1 = r[1] * sc; r2 = r[2] * sc;
+#pragma unroll
+    for (int i = 0; i < 60; ++i) Jl[i] *= sc;
+    if (c.intr_opt != RCVD_INTR_PER_FRAME) { Jl[6] = Jl[26] = Jl[46] = 0.0; Jl[16] = Jl[36] = Jl[56] = 0.0; }
+  }
+  // ---- stage [J_P | r] rows: columns 0..6 frame-0 pose+focal, 7..13 frame-1, 14 = r, 15 = 0 ----
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double* row = Js + (size_t)(tid * 3 + i) * kJsLd;
+#pragma unroll
+    for (int q = 0; q < 7; ++q) { row[q] = Jl[i * 20 + q]; row[7 + q] = Jl[i * 20 + 10 + q]; }
+    row[14] = (i == 0) ? r0 : (i == 1 ? r1 : r2);
+    row[15] = 0.0;
+  }
+  // ---- per-thread scatter of the spline-node columns ----
+  if (active && nn > 0) {
+    const double ca0 = Jl[7], ca1 = Jl[27], ca2 = Jl[47];      // d r / d D0
+    const double cb0 = Jl[17], cb1 = Jl[37], cb2 = Jl[57];     // d r / d D1
+    const double gDa = ca0 * r0 + ca1 * r1 + ca2 * r2, gDb = cb0 * r0 + cb1 * r1 + cb2 * r2;
+    const double mAA = ca0 * ca0 + ca1 * ca1 + ca2 * ca2, mBB = cb0 * cb0 + cb1 * cb1 + cb2 * cb2, mAB = ca0 * cb0 + ca1 * cb1 + ca2 * cb2;
+    double mPa[14], mPb[14];   // M[P, Da], M[P, Db]
+#pragma unroll
+    for (int q = 0; q < 7; ++q) {
+      mPa[q] = Jl[q] * ca0 + Jl[20 + q] * ca1 + Jl[40 + q] * ca2;
+      mPa[7 + q] = Jl[10 + q] * ca0 + Jl[30 + q] * ca1 + Jl[50 + q] * ca2;
+      mPb[q] = Jl[q] * cb0 + Jl[20 + q] * cb1 + Jl[40 + q] * cb2;
+      mPb[7 + q] = Jl[10 + q] * cb0 + Jl[30 + q] * cb1 + Jl[50 + q] * cb2;
+    }
+    const int nphi = (c.intr_opt == RCVD_INTR_PER_FRAME) ? 7 : 6;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i < nn) {
+        const int la = L.offD + idx0[i], lb = L.offD + idx1[i];
+        const double wa = w0[i], wb = w1[i];
+        red_add(g + (size_t)f0 * np + la, gDa * wa);
+        red_add(g + (size_t)f1 * np + lb, gDb * wb);
+        for (int q = 0; q < nphi; ++q) {
+          // node of frame 0 against pose/focal of frame 0 (same block, node row > pose col) and of frame 1 (cross block)
+          red_add(H0 + (size_t)la * np + q, mPa[q] * wa);
+          if (f0rows) red_add(Hx + (size_t)la * np + q, mPa[7 + q] * wa); else red_add(Hx + (size_t)q * np + la, mPa[7 + q] * wa);
+          red_add(H1 + (size_t)lb * np + q, mPb[7 + q] * wb);
+          if (f0rows) red_add(Hx + (size_t)q * np + lb, mPb[q] * wb); else red_add(Hx + (size_t)lb * np + q, mPb[q] * wb);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < nn) {
+            const int la2 = L.offD + idx0[j], lb2 = L.offD + idx1[j];
+            if (la >= la2) red_add(H0 + (size_t)la * np + la2, mAA * wa * w0[j]);
+            if (lb >= lb2) red_add(H1 + (size_t)lb * np + lb2, mBB * wb * w1[j]);
+            if (f0rows) red_add(Hx + (size_t)la * np + lb2, mAB * wa * w1[j]); else red_add(Hx + (size_t)lb2 * np + la, mAB * wa * w1[j]);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- M = J_P^T [J_P | r] over this warp's 96 residual rows on the fp64 tensor cores ----
+  {
+    const int gq = lane >> 2, tq = lane & 3;
+    double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+    const double* base = Js + (size_t)warp * 96 * kJsLd;
+#pragma unroll 4
+    for (int k4 = 0; k4 < 24; ++k4) {
+      const double* rowp = base + (size_t)(k4 * 4 + tq) * kJsLd;
+      const double a0 = rowp[gq], a1 = rowp[8 + gq];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) dmma_acc(acc[i][j][0], acc[i][j][1], i ? a1 : a0, j ? a1 : a0);
+    }
+    double* mw = Ms + warp * 256;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { mw[(i * 8 + gq) * 16 + j * 8 + 2 * tq] = acc[i][j][0]; mw[(i * 8 + gq) * 16 + j * 8 + 2 * tq + 1] = acc[i][j][1]; }
+  }
+  __syncthreads();
+  for (int e = tid; e < 256; e += kTile) {
+    const int i = e >> 4, j = e & 15;
+    if (i >= 14 || j >= 15) continue;
+    const double v = Ms[e] + Ms[256 + e] + Ms[512 + e] + Ms[768 + e];
+    const int fi = i < 7 ? f0 : f1, li = i < 7 ? i : i - 7;
+    if (j == 14) { red_add(g + (size_t)fi * np + li, v); continue; }
+    const bool jf0 = j < 7; const int lj = jf0 ? j : j - 7;
+    if ((i < 7) == jf0) { if (li >= lj) red_add((i < 7 ? H0 : H1) + (size_t)li * np + lj, v); }
+    else if (i < 7) {   // row index in frame 0, column in frame 1: each cross entry appears twice in M (i<7,j>=7 and mirrored); take this one
+      if (f0rows) red_add(Hx + (size_t)li * np + lj, v); else red_add(Hx + (size_t)lj * np + li, v);
+    }
+  }
+  block_store_sum(cost, partial + t);
+}
+
 // Marks parameters referenced by at least one residual block (the Ceres program's
 // parameter set): used for |x| / |step| norms.  mask has npad stride.
 __global__ void __launch_bounds__(kTile) k_mark_static(DevProblem p, uint8_t* __restrict__ mask) {

@@ -125,94 +125,108 @@ __global__ void __launch_bounds__(kPotrfThreads) k_potrf(double* __restrict__ Lb
 
 // ---------------------------------------------------------------------------
 // k_potrf_smem: same factorisation with the whole lower triangle resident in shared memory
-// (npad <= 208: 91 tiles x 16 x 17 doubles = 198 KB of the 227 KB a CTA may use).
+// (npad <= 224: 105 tiles x 2 KB = 210 KB of the 227 KB a CTA may use).  Tiles are 16x16
+// doubles, XOR-swizzled (element (r,k) at r*16 + (k ^ 4*(r&3))) so that the fp64 tensor-core
+// fragment loads of the panel / trailing updates are bank-conflict free without padding.
 // ---------------------------------------------------------------------------
 constexpr int kPotrfSmemThreads = 512;
-constexpr int kTileLd = 17, kTileSz = 16 * kTileLd;
-__host__ __device__ inline size_t potrf_smem_bytes(int npad) { const int nt = npad / 16; return (size_t)(nt * (nt + 1) / 2) * kTileSz * sizeof(double); }
+constexpr int kTileSz = 256;
+__host__ __device__ inline size_t potrf_smem_bytes(int npad) { const int nt = npad / 16; return (size_t)(nt * (nt + 1) / 2 + 1) * kTileSz * sizeof(double); }
+__device__ __forceinline__ int swz(int r, int k) { return r * 16 + (k ^ ((r & 3) << 2)); }
+__device__ __forceinline__ void dmma_8x8x4_fwd(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// C(16x16) = A(16x16) * B(16x16)^T into acc[i8][j8][2] with DMMA; A, B swizzled tiles in smem.
+__device__ __forceinline__ void tile_mma_nt(const double* __restrict__ At, const double* __restrict__ Bt, double acc[2][2][2], int g, int t) {
+#pragma unroll
+  for (int k4 = 0; k4 < 4; ++k4) {
+    double af[2], bf[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { af[i] = At[swz(i * 8 + g, k4 * 4 + t)]; bf[i] = Bt[swz(i * 8 + g, k4 * 4 + t)]; }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) dmma_8x8x4_fwd(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+  }
+}
 
 __global__ void __launch_bounds__(kPotrfSmemThreads) k_potrf_smem(double* __restrict__ Lb, double* __restrict__ invT,
                                                                    const int* __restrict__ frames, int npad, int* __restrict__ fail) {
-  extern __shared__ double tiles[];
-  __shared__ double Di[16][17];
+  extern __shared__ __align__(16) double tiles[];
   const int frame = frames[blockIdx.x];
   double* A = Lb + (size_t)frame * npad * npad;
   double* iT = invT + (size_t)frame * npad * 16;
   const int nt = npad / 16, ntl = nt * (nt + 1) / 2;
+  double* Di = tiles + (size_t)ntl * kTileSz;     // swizzled inverse of the current diagonal tile
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = kPotrfSmemThreads / 32;
-  // load the lower tiles (one 16x16 tile per 256 consecutive work items; rows are 128 B segments)
+  const int g = lane >> 2, t = lane & 3;
   for (int idx = tid; idx < ntl * 256; idx += kPotrfSmemThreads) {
-    const int t = idx >> 8, e = idx & 255, r = e >> 4, c = e & 15;
-    int ti = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
-    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-    while (ti * (ti + 1) / 2 > t) --ti;
-    const int tj = t - ti * (ti + 1) / 2;
-    tiles[(size_t)t * kTileSz + r * kTileLd + c] = A[(size_t)(ti * 16 + r) * npad + tj * 16 + c];
+    const int tl = idx >> 8, e = idx & 255, r = e >> 4, c = e & 15;
+    int ti = (int)((sqrtf(8.f * tl + 1.f) - 1.f) * 0.5f);
+    while ((ti + 1) * (ti + 2) / 2 <= tl) ++ti;
+    while (ti * (ti + 1) / 2 > tl) --ti;
+    const int tj = tl - ti * (ti + 1) / 2;
+    tiles[(size_t)tl * kTileSz + swz(r, c)] = A[(size_t)(ti * 16 + r) * npad + tj * 16 + c];
   }
   __syncthreads();
   for (int jb = 0; jb < nt; ++jb) {
     double* D = tiles + (size_t)(jb * (jb + 1) / 2 + jb) * kTileSz;
     if (warp == 0) {
-      // register-resident right-looking Cholesky of the 16x16 tile: lane i (< 16) owns row i
+      // register-resident right-looking Cholesky of the 16x16 tile: lane i (mod 16) owns row i
       const int i = lane & 15;
       double a[16];
 #pragma unroll
-      for (int c = 0; c < 16; ++c) a[c] = (c <= i) ? D[i * kTileLd + c] : 0.0;
+      for (int c = 0; c < 16; ++c) a[c] = (c <= i) ? D[swz(i, c)] : 0.0;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        double d = __shfl_sync(0xffffffffu, a[j], j);        // pivot a_jj (already updated)
+        double d = __shfl_sync(0xffffffffu, a[j], j);
         if (!(d > 0.0) || !isfinite(d)) { if (lane == 0) *fail = 1; d = 1.0; }
         const double pinv = rsqrt(d);
-        const double lij = (i == j) ? d * pinv : a[j] * pinv;   // l_jj = sqrt(d), l_ij = a_ij / sqrt(d)
+        const double lij = (i == j) ? d * pinv : a[j] * pinv;
         if (i >= j) a[j] = lij;
 #pragma unroll
         for (int c = j + 1; c < 16; ++c) {
-          const double lcj = __shfl_sync(0xffffffffu, a[j], c);  // l_cj (lane c has just stored it)
+          const double lcj = __shfl_sync(0xffffffffu, a[j], c);
           if (i >= c) a[c] -= lij * lcj;
         }
       }
-      // inverse of the triangular tile, lane c = column c: forward substitution with rows broadcast by shuffle
-      {
-        const int cidx = lane & 15;
-        double xcol[16];
+      // inverse of the triangular tile: lane c = column c, rows broadcast by shuffle
+      const int cidx = lane & 15;
+      double xcol[16];
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          double sacc = (r == cidx) ? 1.0 : 0.0;
+      for (int r = 0; r < 16; ++r) {
+        double s0 = (r == cidx) ? 1.0 : 0.0, s1 = 0.0;
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            if (q < r) { const double lrq = __shfl_sync(0xffffffffu, a[q], r); sacc -= lrq * xcol[q]; }
-          }
-          const double lrr = __shfl_sync(0xffffffffu, a[r], r);
-          xcol[r] = (r < cidx) ? 0.0 : sacc / lrr;
+        for (int q = 0; q < 16; ++q) {
+          if (q < r) { const double lrq = __shfl_sync(0xffffffffu, a[q], r); if (q & 1) s1 -= lrq * xcol[q]; else s0 -= lrq * xcol[q]; }
         }
-        if (lane < 16) {
+        const double lrr = __shfl_sync(0xffffffffu, a[r], r);
+        xcol[r] = (r < cidx) ? 0.0 : (s0 + s1) / lrr;
+      }
+      if (lane < 16) {
 #pragma unroll
-          for (int r = 0; r < 16; ++r) { Di[r][cidx] = xcol[r]; iT[(size_t)jb * 256 + r * 16 + cidx] = xcol[r]; }
+        for (int r = 0; r < 16; ++r) { Di[swz(r, cidx)] = xcol[r]; iT[(size_t)jb * 256 + r * 16 + cidx] = xcol[r]; }
 #pragma unroll
-          for (int c = 0; c < 16; ++c) D[i * kTileLd + c] = a[c];
-        }
+        for (int c = 0; c < 16; ++c) D[swz(i, c)] = a[c];
       }
     }
     __syncthreads();
-    // panel: tile(ti, jb) <- tile(ti, jb) * Di^T
+    // panel: tile(ti, jb) <- tile(ti, jb) * Di^T   (fp64 tensor cores)
     for (int ti = jb + 1 + warp; ti < nt; ti += nw) {
       double* Tt = tiles + (size_t)(ti * (ti + 1) / 2 + jb) * kTileSz;
-      const int r = lane >> 1, c0 = (lane & 1) * 8;
-      double a[16];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) a[q] = Tt[r * kTileLd + q];
+      double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+      tile_mma_nt(Tt, Di, acc, g, t);
       __syncwarp();
 #pragma unroll
-      for (int cc = 0; cc < 8; ++cc) {
-        const int c = c0 + cc;
-        double sacc = 0.0;
+      for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int q = 0; q < 16; ++q) if (q <= c) sacc += a[q] * Di[c][q];
-        Tt[r * kTileLd + c] = sacc;
-      }
+        for (int j = 0; j < 2; ++j)
+          *reinterpret_cast<double2*>(&Tt[swz(i * 8 + g, j * 8 + 2 * t)]) = make_double2(acc[i][j][0], acc[i][j][1]);
     }
     __syncthreads();
-    // trailing update: tile(ti, tj) -= X_ti X_tj^T, jb < tj <= ti
+    // trailing update: tile(gi, gj) -= X_gi X_gj^T, jb < gj <= gi   (fp64 tensor cores)
     const int m = nt - jb - 1, ntr = m * (m + 1) / 2;
     for (int tl = warp; tl < ntr; tl += nw) {
       int ti = (int)((sqrtf(8.f * tl + 1.f) - 1.f) * 0.5f);
@@ -223,28 +237,25 @@ __global__ void __launch_bounds__(kPotrfSmemThreads) k_potrf_smem(double* __rest
       const double* Xi = tiles + (size_t)(gi * (gi + 1) / 2 + jb) * kTileSz;
       const double* Xj = tiles + (size_t)(gj * (gj + 1) / 2 + jb) * kTileSz;
       double* Ct = tiles + (size_t)(gi * (gi + 1) / 2 + gj) * kTileSz;
-      const int r = lane >> 1, c0 = (lane & 1) * 8;
-      double acc[8];
+      double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+      tile_mma_nt(Xi, Xj, acc, g, t);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+      for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const double av = Xi[r * kTileLd + q];
-#pragma unroll
-        for (int cc = 0; cc < 8; ++cc) acc[cc] += av * Xj[(c0 + cc) * kTileLd + q];
-      }
-#pragma unroll
-      for (int cc = 0; cc < 8; ++cc) Ct[r * kTileLd + c0 + cc] -= acc[cc];
+        for (int j = 0; j < 2; ++j) {
+          double2* ptr = reinterpret_cast<double2*>(&Ct[swz(i * 8 + g, j * 8 + 2 * t)]);
+          double2 v = *ptr; v.x -= acc[i][j][0]; v.y -= acc[i][j][1]; *ptr = v;
+        }
     }
     __syncthreads();
   }
   for (int idx = tid; idx < ntl * 256; idx += kPotrfSmemThreads) {
-    const int t = idx >> 8, e = idx & 255, r = e >> 4, c = e & 15;
-    int ti = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
-    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-    while (ti * (ti + 1) / 2 > t) --ti;
-    const int tj = t - ti * (ti + 1) / 2;
-    const double v = tiles[(size_t)t * kTileSz + r * kTileLd + c];
+    const int tl = idx >> 8, e = idx & 255, r = e >> 4, c = e & 15;
+    int ti = (int)((sqrtf(8.f * tl + 1.f) - 1.f) * 0.5f);
+    while ((ti + 1) * (ti + 2) / 2 <= tl) ++ti;
+    while (ti * (ti + 1) / 2 > tl) --ti;
+    const int tj = tl - ti * (ti + 1) / 2;
+    const double v = tiles[(size_t)tl * kTileSz + swz(r, c)];
     A[(size_t)(ti * 16 + r) * npad + tj * 16 + c] = (ti == tj && c > r) ? 0.0 : v;
   }
 }
@@ -275,11 +286,14 @@ __global__ void __launch_bounds__(256) k_trinv(const double* __restrict__ Lb, co
     const int kw = (i - j) * 16;
     for (int e = tid; e < 16 * kw; e += 256) { const int rr = e / kw, kk = e % kw; Lrow_s[rr * ldp + kk] = A[(size_t)(i * 16 + rr) * npad + j * 16 + kk]; }
     __syncthreads();
-    double s = 0.0;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     const double* lr = Lrow_s + r * ldp;
     const double* zp = Z + (size_t)j * 256 + c;
-    for (int kk = 0; kk < kw; ++kk) s += lr[kk] * zp[(size_t)kk * 16];
-    W[r][c] = s;
+    for (int kk = 0; kk < kw; kk += 4) {     // kw is a multiple of 16
+      s0 += lr[kk] * zp[(size_t)kk * 16]; s1 += lr[kk + 1] * zp[(size_t)(kk + 1) * 16];
+      s2 += lr[kk + 2] * zp[(size_t)(kk + 2) * 16]; s3 += lr[kk + 3] * zp[(size_t)(kk + 3) * 16];
+    }
+    W[r][c] = (s0 + s1) + (s2 + s3);
     __syncthreads();
     double zv = 0.0;
     const double* ti = iT + (size_t)i * 256;
@@ -296,7 +310,7 @@ __global__ void __launch_bounds__(256) k_trinv(const double* __restrict__ Lb, co
 // fp64 tensor cores (mma.sync m8n8k4 -> DMMA), CTA tile 64x64, 4 warps of 32x32,
 // K staged 16 at a time through a cp.async double buffer.
 // ---------------------------------------------------------------------------
-struct GemmTask { int dst; int first; int count; int lower_only; };
+struct GemmTask { int dst; int first; int count; int lower_only; };   // lower_only bit0: symmetric target (skip tiles above the diagonal); bit1: B is lower triangular
 
 constexpr int kGemmLd = 20;   // padded leading dimension of the 64x16 smem tiles (conflict-free DMMA fragment loads)
 
@@ -313,20 +327,23 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(128) k_gemm_nt(double* __restrict__ dst, const double* __restrict__ Abase, const double* __restrict__ Bbase,
+__global__ void __launch_bounds__(128, 4) k_gemm_nt(double* __restrict__ dst, const double* __restrict__ Abase, const double* __restrict__ Bbase,
                                                   const GemmTask* __restrict__ tasks, const int2* __restrict__ pairs,
                                                   int npad, double alpha, double beta) {
   __shared__ __align__(16) double As[2][64 * kGemmLd];
   __shared__ __align__(16) double Bs[2][64 * kGemmLd];
   const GemmTask task = tasks[blockIdx.z];
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-  if (task.lower_only && n0 > m0) return;   // symmetric target: tiles strictly above the diagonal are never read
+  if ((task.lower_only & 1) && n0 > m0) return;   // symmetric target: tiles strictly above the diagonal are never read
   const size_t bs = (size_t)npad * npad;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
   const int g = lane >> 2, t = lane & 3;
-  const int kchunks = npad / 16;
+  // B lower triangular (inv(L_kk)): B[n][k] = 0 for k > n, so only K chunks up to this tile's last column matter
+  const int kchunks = (task.lower_only & 2) ? min(npad, n0 + 64) / 16 : npad / 16;
   const int total = task.count * kchunks;
+  // 8-row / 8-column mma tiles of this warp that lie inside the matrix (npad is a multiple of 16, tiles are 64)
+  const int ni = min(4, max(0, (npad - (m0 + wm)) / 8)), nj = min(4, max(0, (npad - (n0 + wn)) / 8));
   double acc[4][4][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -365,7 +382,7 @@ __global__ void __launch_bounds__(128) k_gemm_nt(double* __restrict__ dst, const
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        for (int j = 0; j < 4; ++j) if (i < ni && j < nj) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
     __syncthreads();
   }

@@ -151,6 +151,10 @@ class Problem:
         keys = ["frames", "offdiag_factor_blocks", "levels", "h_blocks", "npad", "stride", "tiles", "update_tasks"]
         return dict(zip(keys, list(out)))
 
+    def set_fast_path(self, on=True):
+        """Test hook: False forces the generic accumulate kernel."""
+        _check(self.L.rcvd_debug_set_fast_path(self.h, C.c_int32(1 if on else 0)))
+
     def launch_count(self):
         return int(self.L.rcvd_launch_count(self.h))
 

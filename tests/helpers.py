@@ -19,6 +19,10 @@ VARIANTS = [
     ("bilinear_vertical_huber", dict(depth_type=abi.DEPTH_GRID, depth_grid_x=6, depth_grid_y=4, spatial_type=abi.SPATIAL_VERTICAL_LINEAR,
                                      robust_type=abi.ROBUST_HUBER, robustness=0.05)),
     ("identitydepth_fixposes", dict(depth_type=abi.DEPTH_IDENTITY, fix_poses=1)),
+    ("bilinear_fixedintr_ratio", dict(depth_type=abi.DEPTH_GRID, depth_grid_x=5, depth_grid_y=3, intr_opt=abi.INTR_FIXED,
+                                      static_loss_type=abi.LOSS_REPRO_DEPTH_RATIO)),
+    ("global_euclid", dict(depth_type=abi.DEPTH_GLOBAL, static_loss_type=abi.LOSS_EUCLIDEAN)),
+    ("identitydepth_perframe", dict(depth_type=abi.DEPTH_IDENTITY)),
 ]
 
 

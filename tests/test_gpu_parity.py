@@ -68,6 +68,18 @@ def test_lm_solve_matches_oracle(name, overrides):
     assert rel < 1e-4, rel
 
 
+@pytest.mark.parametrize("name", ["bilinear_perframe_disp", "global_perframe_disp", "bilinear_fixedintr_ratio", "global_euclid", "identitydepth_perframe"])
+def test_fast_kernel_matches_generic(name):
+    overrides = dict(helpers.VARIANTS)[name]
+    sc, cfg, O, G, x = _both(overrides)
+    Hf = G.normal_matrix_dense(); cf, gf = G.evaluate(True)
+    G.set_fast_path(False)
+    Hg = G.normal_matrix_dense(); cg, gg = G.evaluate(True)
+    assert np.abs(Hf - Hg).max() <= 1e-10 * np.abs(Hg).max()
+    assert np.abs(gf - gg).max() <= 1e-10 * max(1.0, np.abs(gg).max())
+    assert abs(cf - cg) <= 1e-12 * abs(cg)
+
+
 def test_normalize_depth_bounded():
     """normalizeDepth problem (lib/PoseOptimizer.cpp:992-1147): scale regulariser only, lower bound 0,
     Armijo line search along the projected path."""
