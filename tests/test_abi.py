@@ -1,0 +1,51 @@
+"""The C-ABI library loads and exports every symbol include/rcvd.h declares (no GPU needed)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "rcvd.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(rcvd_[a-z_0-9]+)\s*\(", txt)))
+
+
+def test_library_exports_declared_symbols():
+    from robust_cvd_b200 import solver
+    L = solver.lib()
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/rcvd.h but not exported"
+
+
+def test_struct_layouts_and_strides():
+    from robust_cvd_b200 import abi, solver
+    assert C.sizeof(abi.Config) == 19 * 4 + 4 + 12 * 8      # 19 int32 + pad + 12 doubles
+    assert C.sizeof(abi.SolveSummary) == 16 + 6 * 8 + 16 + 128
+    L = solver.lib()
+    assert L.rcvd_abi_version() == 1
+    cfg = abi.default_config(4, 1.5, depth_type=abi.DEPTH_GRID, depth_grid_x=17, depth_grid_y=10)
+    assert solver.frame_stride(cfg) == 7 + 170
+    assert solver.depth_param_offset(cfg) == 7 and solver.spatial_param_offset(cfg) == 177
+    cfg2 = abi.default_config(4, 1.5, depth_type=abi.DEPTH_GRID, depth_cubic=0, value_xform=abi.VALUE_SCALESHIFT, depth_grid_x=4, depth_grid_y=4)
+    assert solver.frame_stride(cfg2) == -1      # linear grid + ScaleShift is unusable in the reference as well
+    opt = abi.SolveOptions()
+    L.rcvd_default_solve_options(C.byref(opt))
+    assert (opt.max_iterations, opt.function_tolerance, opt.initial_radius, opt.min_relative_decrease) == (1000, 1e-6, 1e4, 1e-3)
+
+
+def test_no_device_fails_loudly():
+    """Without a CUDA device problem creation must fail (no CPU fallback)."""
+    from robust_cvd_b200 import abi, solver
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback|no usable CUDA device"):
+        solver.Problem(abi.default_config(4, 1.5))
+    with pytest.raises(RuntimeError, match="no CPU fallback|no usable CUDA device"):
+        solver.depth_apply(abi.default_config(1, 1.5), [1.0], [[1.0, 2.0]])

