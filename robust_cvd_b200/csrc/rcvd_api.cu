@@ -172,7 +172,7 @@ __global__ void k_h_to_dense(const double* __restrict__ H, const HBlock* __restr
 }
 
 // ---------------------------------------------------------------------------
-struct Level { int frame_off, nframes; int trsm_off, ntrsm; int upd_off, nupd; int fwd_off, nfwd; };
+struct Level { int frame_off, nframes; int trsm_off, ntrsm; int upd_off, nupd; int upd2_off, nupd2; int fwd_off, nfwd; };   // upd: targets consumed by the next level; upd2: the rest
 
 struct rcvd_problem {
   rcvd_config cfg; Layout L; int N = 0; int device = 0;
@@ -205,7 +205,8 @@ struct rcvd_problem {
   // multi GPU
   int nranks = 1, rank = 0; nccl::Comm comm = nullptr;
   int64_t launches = 0, graph_launches = 0;
-  std::vector<double> h_state; bool state_dirty = false; bool use_fast = true;
+  std::vector<double> h_state; bool state_dirty = false; bool use_fast = true; bool overlap = true;
+  cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   double *d_g2 = nullptr, *d_delta = nullptr; int* h_fail = nullptr;
   cudaEvent_t ev[8] = {nullptr};
   std::vector<void*> allocs;
@@ -276,7 +277,8 @@ static int build_structure(rcvd_problem* p) {
   }
   // L off-diagonal blocks (r later than c)
   std::map<std::pair<int, int>, int> lid; int nLoff = 0;
-  for (int k : order) for (int r : cs[k]) lid[{r, k}] = N + nLoff++;
+  std::vector<int> lcol;   // column (earlier-eliminated) frame of each off-diagonal factor block
+  for (int k : order) for (int r : cs[k]) { lid[{r, k}] = N + nLoff++; lcol.push_back(k); }
   p->nLoff = nLoff;
   // H blocks: diagonal first, then original off-diagonals oriented (later, earlier)
   p->hblocks.clear();
@@ -321,11 +323,19 @@ static int build_structure(rcvd_problem* p) {
         upd[target].push_back(make_int2(lid[{r, k}] - N, lid[{c, k}] - N));
       }
     }
-    for (auto& kv : upd) {
-      upd_tasks.push_back({kv.first, (int)upd_pairs.size(), (int)kv.second.size(), kv.first < N ? 1 : 0});
-      upd_pairs.insert(upd_pairs.end(), kv.second.begin(), kv.second.end());
+    // targets whose column frame is eliminated in the very next level must be complete before that level starts (critical);
+    // all other updates may overlap the next level's potrf / inverse / trsm on a second stream.
+    for (int pass = 0; pass < 2; ++pass) {
+      if (pass == 1) lv.upd2_off = (int)upd_tasks.size();
+      for (auto& kv : upd) {
+        const int cframe = kv.first < N ? kv.first : lcol[kv.first - N];
+        const bool critical = (lvl[cframe] == l + 1);
+        if (critical != (pass == 0)) continue;
+        upd_tasks.push_back({kv.first, (int)upd_pairs.size(), (int)kv.second.size(), kv.first < N ? 1 : 0});
+        upd_pairs.insert(upd_pairs.end(), kv.second.begin(), kv.second.end());
+      }
     }
-    lv.ntrsm = (int)trsm_tasks.size() - lv.trsm_off; lv.nupd = (int)upd_tasks.size() - lv.upd_off; lv.nfwd = (int)fwd_tasks.size() - lv.fwd_off;
+    lv.ntrsm = (int)trsm_tasks.size() - lv.trsm_off; lv.nupd = lv.upd2_off - lv.upd_off; lv.nupd2 = (int)upd_tasks.size() - lv.upd2_off; lv.nfwd = (int)fwd_tasks.size() - lv.fwd_off;
     p->levels.push_back(lv);
   }
   for (int k = 0; k < N; ++k) { col_ptr[k] = (int)col_tasks.size(); for (int r : cs[k]) col_tasks.push_back({lid[{r, k}] - N, r, k}); }
@@ -408,7 +418,12 @@ static int enqueue_factor_solve(rcvd_problem* p) {
   const int tiles = (npad + 63) / 64;
   k_load_factor<<<dim3((npad * npad + 255) / 256, nL), 256, 0, st>>>(p->d_H, p->d_Lb, p->d_lblocks, p->d_S, p->d_D2, npad, L.nf);
   p->launches += 1;
-  for (const Level& lv : p->levels) {
+  // Two-stream schedule (fork/join inside the captured graph): the non-critical update GEMMs of level l run on `side`
+  // concurrently with potrf / inverse / trsm of level l+1 on `st`.
+  cudaStream_t side = p->side_stream;
+  bool side_pending = false;
+  for (size_t li = 0; li < p->levels.size(); ++li) {
+    const Level& lv = p->levels[li];
     if (potrf_smem_bytes(npad) <= 220 * 1024)
       k_potrf_smem<<<lv.nframes, kPotrfSmemThreads, potrf_smem_bytes(npad), st>>>(p->d_Lb, p->d_invT, p->d_lvl_frames + lv.frame_off, npad, p->d_fail);
     else
@@ -416,8 +431,18 @@ static int enqueue_factor_solve(rcvd_problem* p) {
     k_trinv<<<dim3(npad / 16, lv.nframes), 256, (npad * 16 + 16 * (npad + 1)) * sizeof(double), st>>>(p->d_Lb, p->d_invT, p->d_invL, p->d_lvl_frames + lv.frame_off, npad);
     p->launches += 2;
     if (lv.ntrsm > 0) { k_gemm_nt<<<dim3(tiles, tiles, lv.ntrsm), 128, 0, st>>>(p->d_T, p->d_Lb, p->d_invL, p->d_trsm_tasks + lv.trsm_off, p->d_trsm_pairs, npad, 1.0, 0.0); p->launches++; }
+    if (lv.nupd2 > 0 && p->overlap) {
+      CK(cudaEventRecord(p->ev_fork, st)); CK(cudaStreamWaitEvent(side, p->ev_fork, 0));
+    }
+    if (side_pending) { CK(cudaStreamWaitEvent(st, p->ev_join, 0)); side_pending = false; }   // U2(l-1) before U1(l)
     if (lv.nupd > 0) { k_gemm_nt<<<dim3(tiles, tiles, lv.nupd), 128, 0, st>>>(p->d_Lb, p->d_T, p->d_T, p->d_upd_tasks + lv.upd_off, p->d_upd_pairs, npad, -1.0, 1.0); p->launches++; }
+    if (lv.nupd2 > 0) {
+      cudaStream_t us = p->overlap ? side : st;
+      k_gemm_nt<<<dim3(tiles, tiles, lv.nupd2), 128, 0, us>>>(p->d_Lb, p->d_T, p->d_T, p->d_upd_tasks + lv.upd2_off, p->d_upd_pairs, npad, -1.0, 1.0); p->launches++;
+      if (p->overlap) { CK(cudaEventRecord(p->ev_join, side)); side_pending = true; }
+    }
   }
+  if (side_pending) CK(cudaStreamWaitEvent(st, p->ev_join, 0));
   CK(cudaMemcpyAsync(p->d_rhs, p->d_gs, (size_t)N * npad * sizeof(double), cudaMemcpyDeviceToDevice, st));
   for (const Level& lv : p->levels) {
     k_fwd_diag<<<dim3((npad + 7) / 8, lv.nframes), 256, 0, st>>>(p->d_invL, p->d_rhs, p->d_ytmp, p->d_lvl_frames + lv.frame_off, npad);
@@ -805,6 +830,9 @@ RCVD_API int32_t rcvd_problem_create(const rcvd_config* cfg, int32_t device, rcv
   rcvd_problem* p = new rcvd_problem();
   p->cfg = *cfg; p->L = L; p->N = cfg->num_frames; p->device = device;
   e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->side_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming);
   if (e != cudaSuccess) { delete p; return set_err(RCVD_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
   *out = p; return RCVD_OK;
 }
@@ -814,6 +842,9 @@ RCVD_API void rcvd_problem_destroy(rcvd_problem* p) {
   free_all(p);
   for (int i = 0; i < 8; ++i) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
   if (p->comm && nccl::CommDestroy) nccl::CommDestroy(p->comm);
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->ev_join) cudaEventDestroy(p->ev_join);
+  if (p->side_stream) cudaStreamDestroy(p->side_stream);
   if (p->stream) cudaStreamDestroy(p->stream);
   delete p;
 }
@@ -975,6 +1006,8 @@ RCVD_API int32_t rcvd_time_iteration(rcvd_problem* p, int32_t iters, double radi
 }
 RCVD_API int64_t rcvd_launch_count(rcvd_problem* p) { return p ? p->launches : 0; }
 // Test hook: 0 forces the generic accumulate kernel, 1 (default) allows the specialised one.
+// Test / bench hook: 0 = single-stream factorisation graph, 1 (default) = overlap non-critical updates on a second stream.
+RCVD_API int32_t rcvd_debug_set_overlap(rcvd_problem* p, int32_t on) { if (!p) return RCVD_ERR_INVALID; p->overlap = on != 0; if (p->solve_graph) { cudaGraphExecDestroy(p->solve_graph); p->solve_graph = nullptr; } return RCVD_OK; }
 RCVD_API int32_t rcvd_debug_set_fast_path(rcvd_problem* p, int32_t on) { if (!p) return RCVD_ERR_INVALID; p->use_fast = on != 0; return RCVD_OK; }
 RCVD_API int32_t rcvd_solve(rcvd_problem* p, const rcvd_solve_options* opt, rcvd_solve_summary* summary) {
   if (!p || !summary) return set_err(RCVD_ERR_INVALID, "null argument");
@@ -988,7 +1021,7 @@ RCVD_API int32_t rcvd_structure_info(rcvd_problem* p, int32_t out[8]) {
   CK(cudaSetDevice(p->device));
   int rc = ensure_ready(p); if (rc) return rc;
   out[0] = p->N; out[1] = p->nLoff; out[2] = (int)p->levels.size(); out[3] = p->nHblocks; out[4] = p->L.npad; out[5] = p->L.nf; out[6] = p->num_tiles;
-  int upd = 0; for (auto& l : p->levels) upd += l.nupd; out[7] = upd;
+  int upd = 0; for (auto& l : p->levels) upd += l.nupd + l.nupd2; out[7] = upd;
   return RCVD_OK;
 }
 

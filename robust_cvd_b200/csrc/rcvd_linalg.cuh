@@ -152,6 +152,33 @@ __device__ __forceinline__ void tile_mma_nt(const double* __restrict__ At, const
   }
 }
 
+// Register-resident right-looking Cholesky of one 16x16 tile by a single warp (lane i mod 16 owns row i).
+// Writes L back to the swizzled tile and the reciprocal pivots 1/l_jj to pinv[0..15].
+__device__ __forceinline__ void warp_chol16(double* __restrict__ D, double* __restrict__ pinv, int lane, int* __restrict__ fail) {
+  const int i = lane & 15;
+  double a[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) a[c] = (c <= i) ? D[swz(i, c)] : 0.0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    double d = __shfl_sync(0xffffffffu, a[j], j);
+    if (!(d > 0.0) || !isfinite(d)) { if (lane == 0) *fail = 1; d = 1.0; }
+    const double pi = rsqrt(d);
+    const double lij = (i == j) ? d * pi : a[j] * pi;
+    if (i >= j) a[j] = lij;
+    if (lane == 0) pinv[j] = pi;
+#pragma unroll
+    for (int c = j + 1; c < 16; ++c) {
+      const double lcj = __shfl_sync(0xffffffffu, a[j], c);
+      if (i >= c) a[c] -= lij * lcj;
+    }
+  }
+  if (lane < 16) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) D[swz(i, c)] = a[c];
+  }
+}
+
 __global__ void __launch_bounds__(kPotrfSmemThreads) k_potrf_smem(double* __restrict__ Lb, double* __restrict__ invT,
                                                                    const int* __restrict__ frames, int npad, int* __restrict__ fail) {
   extern __shared__ __align__(16) double tiles[];
@@ -159,7 +186,7 @@ __global__ void __launch_bounds__(kPotrfSmemThreads) k_potrf_smem(double* __rest
   double* A = Lb + (size_t)frame * npad * npad;
   double* iT = invT + (size_t)frame * npad * 16;
   const int nt = npad / 16, ntl = nt * (nt + 1) / 2;
-  double* Di = tiles + (size_t)ntl * kTileSz;     // swizzled inverse of the current diagonal tile
+  double* pinv = tiles + (size_t)ntl * kTileSz;     // [npad] reciprocal pivots (fits the spare 2 KB tile for npad <= 256)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = kPotrfSmemThreads / 32;
   const int g = lane >> 2, t = lane & 3;
   for (int idx = tid; idx < ntl * 256; idx += kPotrfSmemThreads) {
@@ -171,64 +198,47 @@ __global__ void __launch_bounds__(kPotrfSmemThreads) k_potrf_smem(double* __rest
     tiles[(size_t)tl * kTileSz + swz(r, c)] = A[(size_t)(ti * 16 + r) * npad + tj * 16 + c];
   }
   __syncthreads();
+  if (warp == 0) warp_chol16(tiles, pinv, lane, fail);
+  __syncthreads();
   for (int jb = 0; jb < nt; ++jb) {
-    double* D = tiles + (size_t)(jb * (jb + 1) / 2 + jb) * kTileSz;
-    if (warp == 0) {
-      // register-resident right-looking Cholesky of the 16x16 tile: lane i (mod 16) owns row i
-      const int i = lane & 15;
+    const double* D = tiles + (size_t)(jb * (jb + 1) / 2 + jb) * kTileSz;
+    const double* pv = pinv + jb * 16;
+    // ---- panel by forward substitution (one thread per row below the tile); warp nw-1 computes the tile inverse ----
+    const int rows = (nt - jb - 1) * 16;
+    if (tid < rows) {
+      const int ti = jb + 1 + (tid >> 4), r = tid & 15;
+      double* Tt = tiles + (size_t)(ti * (ti + 1) / 2 + jb) * kTileSz;
       double a[16];
 #pragma unroll
-      for (int c = 0; c < 16; ++c) a[c] = (c <= i) ? D[swz(i, c)] : 0.0;
+      for (int q = 0; q < 16; ++q) a[q] = Tt[swz(r, q)];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        double d = __shfl_sync(0xffffffffu, a[j], j);
-        if (!(d > 0.0) || !isfinite(d)) { if (lane == 0) *fail = 1; d = 1.0; }
-        const double pinv = rsqrt(d);
-        const double lij = (i == j) ? d * pinv : a[j] * pinv;
-        if (i >= j) a[j] = lij;
+      for (int c = 0; c < 16; ++c) {
+        double sacc = a[c];
 #pragma unroll
-        for (int c = j + 1; c < 16; ++c) {
-          const double lcj = __shfl_sync(0xffffffffu, a[j], c);
-          if (i >= c) a[c] -= lij * lcj;
-        }
+        for (int q = 0; q < 16; ++q) if (q < c) sacc -= a[q] * D[swz(c, q)];
+        a[c] = sacc * pv[c];
       }
-      // inverse of the triangular tile: lane c = column c, rows broadcast by shuffle
-      const int cidx = lane & 15;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) Tt[swz(r, q)] = a[q];
+    } else if (warp == nw - 1 && lane < 16) {
+      // inverse of the triangular tile (only needed by k_trinv): column `lane`, forward substitution
+      const int cidx = lane;
       double xcol[16];
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
         double s0 = (r == cidx) ? 1.0 : 0.0, s1 = 0.0;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          if (q < r) { const double lrq = __shfl_sync(0xffffffffu, a[q], r); if (q & 1) s1 -= lrq * xcol[q]; else s0 -= lrq * xcol[q]; }
-        }
-        const double lrr = __shfl_sync(0xffffffffu, a[r], r);
-        xcol[r] = (r < cidx) ? 0.0 : (s0 + s1) / lrr;
+        for (int q = 0; q < 16; ++q) if (q < r) { const double lrq = D[swz(r, q)]; if (q & 1) s1 -= lrq * xcol[q]; else s0 -= lrq * xcol[q]; }
+        xcol[r] = (r < cidx) ? 0.0 : (s0 + s1) * pv[r];
       }
-      if (lane < 16) {
 #pragma unroll
-        for (int r = 0; r < 16; ++r) { Di[swz(r, cidx)] = xcol[r]; iT[(size_t)jb * 256 + r * 16 + cidx] = xcol[r]; }
-#pragma unroll
-        for (int c = 0; c < 16; ++c) D[swz(i, c)] = a[c];
-      }
+      for (int r = 0; r < 16; ++r) iT[(size_t)jb * 256 + r * 16 + cidx] = xcol[r];
     }
     __syncthreads();
-    // panel: tile(ti, jb) <- tile(ti, jb) * Di^T   (fp64 tensor cores)
-    for (int ti = jb + 1 + warp; ti < nt; ti += nw) {
-      double* Tt = tiles + (size_t)(ti * (ti + 1) / 2 + jb) * kTileSz;
-      double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
-      tile_mma_nt(Tt, Di, acc, g, t);
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-          *reinterpret_cast<double2*>(&Tt[swz(i * 8 + g, j * 8 + 2 * t)]) = make_double2(acc[i][j][0], acc[i][j][1]);
-    }
-    __syncthreads();
-    // trailing update: tile(gi, gj) -= X_gi X_gj^T, jb < gj <= gi   (fp64 tensor cores)
+    // ---- trailing update (DMMA) with lookahead: warp 0 updates tile (jb+1, jb+1) first and factors it at once ----
     const int m = nt - jb - 1, ntr = m * (m + 1) / 2;
     for (int tl = warp; tl < ntr; tl += nw) {
+      // tile order: tl = 0 is (jb+1, jb+1) and goes to warp 0
       int ti = (int)((sqrtf(8.f * tl + 1.f) - 1.f) * 0.5f);
       while ((ti + 1) * (ti + 2) / 2 <= tl) ++ti;
       while (ti * (ti + 1) / 2 > tl) --ti;
@@ -246,6 +256,7 @@ __global__ void __launch_bounds__(kPotrfSmemThreads) k_potrf_smem(double* __rest
           double2* ptr = reinterpret_cast<double2*>(&Ct[swz(i * 8 + g, j * 8 + 2 * t)]);
           double2 v = *ptr; v.x -= acc[i][j][0]; v.y -= acc[i][j][1]; *ptr = v;
         }
+      if (tl == 0) { __syncwarp(); warp_chol16(Ct, pinv + (jb + 1) * 16, lane, fail); }   // lookahead: next diagonal tile
     }
     __syncthreads();
   }
