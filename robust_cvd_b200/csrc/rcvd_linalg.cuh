@@ -133,6 +133,10 @@ constexpr int kPotrfSmemThreads = 512;
 constexpr int kTileSz = 256;
 __host__ __device__ inline size_t potrf_smem_bytes(int npad) { const int nt = npad / 16; return (size_t)(nt * (nt + 1) / 2 + 1) * kTileSz * sizeof(double); }
 __device__ __forceinline__ int swz(int r, int k) { return r * 16 + (k ^ ((r & 3) << 2)); }
+__device__ __forceinline__ void cp_async16_fwd(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void dmma_8x8x4_fwd(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
@@ -168,9 +172,11 @@ __device__ __forceinline__ void warp_chol16(double* __restrict__ D, double* __re
     if (i >= j) a[j] = lij;
     if (lane == 0) pinv[j] = pi;
 #pragma unroll
-    for (int c = j + 1; c < 16; ++c) {
-      const double lcj = __shfl_sync(0xffffffffu, a[j], c);
-      if (i >= c) a[c] -= lij * lcj;
+    for (int c = 0; c < 16; ++c) {
+      if (c > j) {   // constant trip count so that a[] stays in registers
+        const double lcj = __shfl_sync(0xffffffffu, a[j], c);
+        if (i >= c) a[c] -= lij * lcj;
+      }
     }
   }
   if (lane < 16) {
@@ -189,14 +195,17 @@ __global__ void __launch_bounds__(kPotrfSmemThreads) k_potrf_smem(double* __rest
   double* pinv = tiles + (size_t)ntl * kTileSz;     // [npad] reciprocal pivots (fits the spare 2 KB tile for npad <= 256)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = kPotrfSmemThreads / 32;
   const int g = lane >> 2, t = lane & 3;
-  for (int idx = tid; idx < ntl * 256; idx += kPotrfSmemThreads) {
-    const int tl = idx >> 8, e = idx & 255, r = e >> 4, c = e & 15;
+  // asynchronous tile load: 16-byte chunks (the swizzle keeps aligned pairs together), all in flight at once
+  for (int idx = tid; idx < ntl * 128; idx += kPotrfSmemThreads) {
+    const int tl = idx >> 7, e = idx & 127, r = e >> 3, c = (e & 7) * 2;
     int ti = (int)((sqrtf(8.f * tl + 1.f) - 1.f) * 0.5f);
     while ((ti + 1) * (ti + 2) / 2 <= tl) ++ti;
     while (ti * (ti + 1) / 2 > tl) --ti;
     const int tj = tl - ti * (ti + 1) / 2;
-    tiles[(size_t)tl * kTileSz + swz(r, c)] = A[(size_t)(ti * 16 + r) * npad + tj * 16 + c];
+    cp_async16_fwd(&tiles[(size_t)tl * kTileSz + swz(r, c)], &A[(size_t)(ti * 16 + r) * npad + tj * 16 + c]);
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   if (warp == 0) warp_chol16(tiles, pinv, lane, fail);
   __syncthreads();
@@ -260,14 +269,15 @@ __global__ void __launch_bounds__(kPotrfSmemThreads) k_potrf_smem(double* __rest
     }
     __syncthreads();
   }
-  for (int idx = tid; idx < ntl * 256; idx += kPotrfSmemThreads) {
-    const int tl = idx >> 8, e = idx & 255, r = e >> 4, c = e & 15;
+  for (int idx = tid; idx < ntl * 128; idx += kPotrfSmemThreads) {
+    const int tl = idx >> 7, e = idx & 127, r = e >> 3, c = (e & 7) * 2;
     int ti = (int)((sqrtf(8.f * tl + 1.f) - 1.f) * 0.5f);
     while ((ti + 1) * (ti + 2) / 2 <= tl) ++ti;
     while (ti * (ti + 1) / 2 > tl) --ti;
     const int tj = tl - ti * (ti + 1) / 2;
-    const double v = tiles[(size_t)tl * kTileSz + swz(r, c)];
-    A[(size_t)(ti * 16 + r) * npad + tj * 16 + c] = (ti == tj && c > r) ? 0.0 : v;
+    double2 v = *reinterpret_cast<const double2*>(&tiles[(size_t)tl * kTileSz + swz(r, c)]);
+    if (ti == tj) { if (c > r) v.x = 0.0; if (c + 1 > r) v.y = 0.0; }
+    *reinterpret_cast<double2*>(&A[(size_t)(ti * 16 + r) * npad + tj * 16 + c]) = v;
   }
 }
 
@@ -338,6 +348,24 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// One 16-deep K stage of a warp's (NI*8) x (NJ*8) sub-tile: NI/NJ are compile-time so that no tensor instruction is predicated
+// (a predicated mma.sync costs a WARPSYNC + branch pair each).
+template <int NI, int NJ>
+__device__ __forceinline__ void gemm_stage(const double* __restrict__ as, const double* __restrict__ bsm, double (&acc)[4][4][2], int wm, int wn, int g, int t) {
+#pragma unroll
+  for (int k4 = 0; k4 < 4; ++k4) {
+    double af[NI > 0 ? NI : 1], bf[NJ > 0 ? NJ : 1];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) af[i] = as[(wm + i * 8 + g) * kGemmLd + k4 * 4 + t];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) bf[j] = bsm[(wn + j * 8 + g) * kGemmLd + k4 * 4 + t];
+#pragma unroll
+    for (int i = 0; i < NI; ++i)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+  }
+}
+
 __global__ void __launch_bounds__(128, 4) k_gemm_nt(double* __restrict__ dst, const double* __restrict__ Abase, const double* __restrict__ Bbase,
                                                   const GemmTask* __restrict__ tasks, const int2* __restrict__ pairs,
                                                   int npad, double alpha, double beta) {
@@ -383,18 +411,11 @@ __global__ void __launch_bounds__(128, 4) k_gemm_nt(double* __restrict__ dst, co
     if (kk + 1 < total) { load_stage(st ^ 1, kk + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();
     const double* as = As[st]; const double* bsm = Bs[st];
-#pragma unroll
-    for (int k4 = 0; k4 < 4; ++k4) {
-      double af[4], bf[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) af[i] = as[(wm + i * 8 + g) * kGemmLd + k4 * 4 + t];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) bf[j] = bsm[(wn + j * 8 + g) * kGemmLd + k4 * 4 + t];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) if (i < ni && j < nj) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-    }
+    // warp-uniform dispatch on the number of in-range 8-wide mma tiles (npad is a multiple of 16 -> ni, nj in {0, 2, 4})
+    if (ni == 4 && nj == 4) gemm_stage<4, 4>(as, bsm, acc, wm, wn, g, t);
+    else if (ni == 4 && nj == 2) gemm_stage<4, 2>(as, bsm, acc, wm, wn, g, t);
+    else if (ni == 2 && nj == 4) gemm_stage<2, 4>(as, bsm, acc, wm, wn, g, t);
+    else if (ni == 2 && nj == 2) gemm_stage<2, 2>(as, bsm, acc, wm, wn, g, t);
     __syncthreads();
   }
   double* C = dst + (size_t)task.dst * bs;
