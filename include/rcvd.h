@@ -18,6 +18,7 @@
  *   addSpatialDeformRegularization (:1497-1522),|
  *   addFocalRegularization (:1524-1549),        |
  *   addPositionRegularization (:1417-1447)      |
+ *   addSceneFlowSmoothnessLoss (:1242-1339)     | rcvd_problem_set_triplets
  *   poseParams_ / xform params_ (:748-783)      | rcvd_problem_set_state / get_state
  *   ceres::Solve (:954-962, :1117-1125)         | rcvd_solve
  *
@@ -50,6 +51,8 @@ enum { RCVD_LOSS_EUCLIDEAN = 0, RCVD_LOSS_REPRO_DISPARITY = 1, RCVD_LOSS_REPRO_D
  * ceres::CauchyLoss(robustness) (lib/PoseOptimizer.cpp:1219-1220).  Huber is an
  * extension (BASELINE.json config 4) with no reference behaviour. */
 enum { RCVD_ROBUST_TRIVIAL = 0, RCVD_ROBUST_CAUCHY = 1, RCVD_ROBUST_HUBER = 2 };
+/* SmoothLossType of the scene-flow smoothness loss (lib/PoseOptimizer.h:37-42) */
+enum { RCVD_SMOOTH_EUCLIDEAN_LAPLACIAN = 0, RCVD_SMOOTH_REPRO_DISPARITY_LAPLACIAN = 1, RCVD_SMOOTH_REPRO_DEPTH_RATIO_CONSISTENCY = 2, RCVD_SMOOTH_REPRO_LOG_DEPTH_CONSISTENCY = 3 };
 
 enum {
   RCVD_OK = 0,
@@ -80,7 +83,7 @@ typedef struct rcvd_config {
   int32_t fix_poses, fix_depth_xforms, fix_spatial_xforms;  /* lib/PoseOptimizer.cpp:915-948 */
   int32_t depth_lower_bound; /* normalizeDepth: lower bound 0 on param 0 of every depth block (:1108-1115) */
   int32_t scale_grid_x, scale_grid_y;     /* scale-regulariser lattice (:1346-1351) */
-  int32_t reserved0;
+  int32_t smooth_loss_type;  /* RCVD_SMOOTH_* (only read when triplet constraints are set) */
   double aspect;             /* double(video.aspect()) (float -> double, :1155) */
   double fixed_vfocal;       /* focalLong/aspect for landscape (:1156-1157) */
   double robustness;         /* Cauchy/Huber scale a */
@@ -162,6 +165,13 @@ int32_t rcvd_problem_set_frames(rcvd_problem* p, const uint8_t* in_range,
  * ndc1.x, ndc1.y, depth1} as float32 (Observation, :104-117). */
 int32_t rcvd_problem_set_constraints(rcvd_problem* p, int32_t num_pairs, const int32_t* pair_frames,
                                      const int64_t* offsets, const float* records);
+
+/* Scene-flow smoothness constraints (addSceneFlowSmoothnessLoss, lib/PoseOptimizer.cpp:1242-1339), grouped by the centre
+ * frame f of the triplet (f-1, f, f+1): centers[T], offsets[T+1], records[n][10] float32 =
+ * {ndc.x, ndc.y, depth} for the three observations + the ScaledLoss weight (smoothStaticWeight or
+ * smoothDynamicWeight, :1314-1317).  Optional; absent by default as in the reference (both weights 0). */
+int32_t rcvd_problem_set_triplets(rcvd_problem* p, int32_t num_groups, const int32_t* centers,
+                                  const int64_t* offsets, const float* records);
 
 /* Multi-GPU: this rank only holds a shard of the pairs; accumulated normal
  * equations and costs are all-reduced over `nranks` ranks with NCCL.

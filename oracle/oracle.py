@@ -73,6 +73,20 @@ class OracleProblem:
         self.num_constraints = int(rec.shape[0])
         self.L.orc_problem_set_constraints(self.h, C.c_int32(pf.shape[0]), _p(pf, C.c_int32), _p(off, C.c_int64), _p(rec, C.c_float))
 
+    def set_triplets(self, centers, offsets, records):
+        """Scene-flow smoothness constraints: centers[T] (middle frame), offsets[T+1], records[n][10] =
+        3 x (ndc.x, ndc.y, depth) + weight (smoothStaticWeight or smoothDynamicWeight)."""
+        ce = np.ascontiguousarray(centers, np.int32); off = np.ascontiguousarray(offsets, np.int64)
+        rec = np.ascontiguousarray(records, np.float32).reshape(-1, 10)
+        assert off.shape[0] == ce.shape[0] + 1 and off[-1] == rec.shape[0]
+        self.num_triplets = int(rec.shape[0])
+        self.L.orc_problem_set_triplets(self.h, C.c_int32(ce.shape[0]), _p(ce, C.c_int32), _p(off, C.c_int64), _p(rec, C.c_float))
+
+    def triplet_jacobian(self):
+        r = np.zeros(3 * self.num_triplets, np.float64); J = np.zeros((3 * self.num_triplets, self.U), np.float64)
+        self.L.orc_triplet_jacobian(self.h, _p(r, C.c_double), _p(J, C.c_double))
+        return r, J
+
     def set_state(self, x):
         x = np.ascontiguousarray(x, np.float64).reshape(-1)
         assert x.size == self.U

@@ -336,6 +336,51 @@ inline void staticSceneCost(const rcvd_config& c, int k, const ObsData& o0, cons
   }
 }
 
+// SceneFlowSmoothnessLoss::operator(), lib/PoseOptimizer.cpp:332-413.  x stacked in Ceres block order:
+//   [pose0, depth0 blocks, spatial0 blocks, pose1, ..., pose2, ..., focal(s)]
+template <class T>
+inline void sceneFlowSmoothnessLoss(const rcvd_config& c, int k, const ObsData& o0, const ObsData& o1, const ObsData& o2, const T* x, T r[3]) {
+  const ObsData* obs[3] = {&o0, &o1, &o2};
+  const T* pose[3]; T pc[3][3];
+  int off = 0;
+  for (int i = 0; i < 3; ++i) {
+    pose[i] = x + off; off += 6;
+    const T* d = x + off; off += obs[i]->dg.n * k;
+    const T* s = x + off; off += obs[i]->sg.n * 2;
+    T warp[2];
+    const T depth = depthFunctor(c, k, obs[i]->dg, obs[i]->depth, d);
+    spatialFunctor(obs[i]->sg, s, warp);
+    pc[i][0] = T(double(obs[i]->ndcx)) + warp[0]; pc[i][1] = T(double(obs[i]->ndcy)) + warp[1]; pc[i][2] = depth;
+  }
+  T focal[3][2];
+  if (c.intr_opt == RCVD_INTR_SHARED) { focal[0][1] = focal[1][1] = focal[2][1] = x[off++]; }
+  else if (c.intr_opt == RCVD_INTR_PER_FRAME) { focal[0][1] = x[off++]; focal[1][1] = x[off++]; focal[2][1] = x[off++]; }
+  else { focal[0][1] = focal[1][1] = focal[2][1] = T(c.fixed_vfocal); }
+  for (int i = 0; i < 3; ++i) focal[i][0] = focal[i][1] * c.aspect;
+  const int lt = c.smooth_loss_type;   // SmoothLossType
+  if (lt == 0) {   // EuclideanLaplacian
+    T w0[3], w1[3], w2[3];
+    cameraToWorld(pc[0], focal[0], pose[0], w0); cameraToWorld(pc[1], focal[1], pose[1], w1); cameraToWorld(pc[2], focal[2], pose[2], w2);
+    for (int i = 0; i < 3; ++i) r[i] = w0[i] + w2[i] - 2.0 * w1[i];
+    return;
+  }
+  T w0[3], w2[3], p01[3], p21[3];
+  cameraToWorld(pc[0], focal[0], pose[0], w0); cameraToWorld(pc[2], focal[2], pose[2], w2);
+  worldToCamera(w0, focal[1], pose[1], p01); worldToCamera(w2, focal[1], pose[1], p21);
+  r[0] = (p01[0] + p21[0] - pc[1][0] * 2.0) / focal[1][1];
+  r[1] = (p01[1] + p21[1] - pc[1][1] * 2.0) / focal[1][1];
+  if (lt == 1) {   // ReproDisparityLaplacian
+    const T eps(1e-6);
+    const T a = 1.0 / jmax(p01[2], eps), b = 1.0 / jmax(pc[1][2], eps), cc = 1.0 / jmax(p21[2], eps);
+    r[2] = a + cc - b * 2.0;
+  } else {
+    const T base = pc[1][2];
+    const T other = p01[2] + p21[2] - pc[1][2];
+    const T mx = jmax(base, other), mn = jmin(base, other);
+    if (lt == 2) r[2] = (mx / mn - 1.0); else r[2] = jlog(mn / mx);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Analytic Jacobian of the same functor (independent derivation, used for the
 // fast CPU baseline "B-analytic" and cross-checked against the Jet version).
@@ -480,6 +525,7 @@ struct Problem {
   std::vector<int32_t> pairFrames;
   std::vector<int64_t> offsets;
   std::vector<float> records;
+  std::vector<int32_t> tripCenters; std::vector<int64_t> tripOffsets; std::vector<float> tripRecords;   // [n][10]: 3 x (ndc.xy, depth), weight
   std::vector<float> scaleLocs;   // lattice (x,y) float32, computed as lib/PoseOptimizer.cpp:1384-1385
   std::vector<double> x;          // N*nf
   // block-sparse normal matrix: lower blocks (r>=c by frame id), full n x n row-major
@@ -774,6 +820,39 @@ static void positionRows(const Problem& P, Sink&& sink) {
   }
 }
 
+// Scene-flow smoothness blocks (addSceneFlowSmoothnessLoss, lib/PoseOptimizer.cpp:1242-1339): evaluated with Jet<4> passes in
+// both Jacobian modes (the literal functor is the only CPU implementation; the CUDA kernel's analytic Jacobian is checked
+// against it).  ScaledLoss(nullptr, w): residual and Jacobian scaled by sqrt(w), cost 1/2 w |r|^2.
+static int tripletCols(const Problem& P, int fc, const ObsData o[3], int* cols) {
+  const Layout& L = P.L; const int n = L.nf; int m = 0;
+  for (int i = 0; i < 3; ++i) {
+    const int f = fc - 1 + i;
+    for (int q = 0; q < 6; ++q) cols[m++] = f * n + q;
+    for (int q = 0; q < o[i].dg.n; ++q) for (int j = 0; j < L.k; ++j) cols[m++] = f * n + L.offD + o[i].dg.idx[q] * L.k + j;
+    for (int q = 0; q < o[i].sg.n; ++q) for (int j = 0; j < 2; ++j) cols[m++] = f * n + L.offS + o[i].sg.idx[q] * 2 + j;
+  }
+  if (P.cfg.intr_opt == RCVD_INTR_SHARED) cols[m++] = 6;
+  else if (P.cfg.intr_opt == RCVD_INTR_PER_FRAME) { cols[m++] = (fc - 1) * n + 6; cols[m++] = fc * n + 6; cols[m++] = (fc + 1) * n + 6; }
+  return m;
+}
+constexpr int kMaxPT = 240;
+static int evalTriplet(const Problem& P, int fc, const float* rec, bool wantJ, double r[3], double* J /*3*kMaxPT*/, int* cols) {
+  const rcvd_config& c = P.cfg; const Layout& L = P.L;
+  ObsData o[3]; for (int i = 0; i < 3; ++i) makeObs(c, rec + 3 * i, o[i]);
+  const int Pn = tripletCols(P, fc, o, cols);
+  double xl[kMaxPT]; for (int i = 0; i < Pn; ++i) xl[i] = P.x[cols[i]];
+  if (!wantJ) { sceneFlowSmoothnessLoss<double>(c, L.k, o[0], o[1], o[2], xl, r); return Pn; }
+  using J4 = Jet<4>; J4 xj[kMaxPT], rj[3];
+  for (int start = 0; start < Pn; start += 4) {
+    for (int i = 0; i < Pn; ++i) xj[i] = J4(xl[i]);
+    for (int q = 0; q < 4 && start + q < Pn; ++q) xj[start + q].v[q] = 1.0;
+    sceneFlowSmoothnessLoss<J4>(c, L.k, o[0], o[1], o[2], xj, rj);
+    for (int q = 0; q < 4 && start + q < Pn; ++q) for (int i = 0; i < 3; ++i) J[i * kMaxPT + start + q] = rj[i].v[q];
+  }
+  for (int i = 0; i < 3; ++i) r[i] = rj[i].a;
+  return Pn;
+}
+
 static void buildStructure(Problem& P) {
   P.H.clear();
   for (int f = 0; f < P.N; ++f) ensureBlock(P, f, f);
@@ -784,6 +863,7 @@ static void buildStructure(Problem& P) {
     ensureBlock(P, a, b);
     if (P.cfg.intr_opt == RCVD_INTR_SHARED) { ensureBlock(P, a, 0); ensureBlock(P, b, 0); }
   }
+  for (size_t t = 0; t < P.tripCenters.size(); ++t) { const int f = P.tripCenters[t]; if (P.tripOffsets[t + 1] > P.tripOffsets[t]) { ensureBlock(P, f - 1, f); ensureBlock(P, f - 1, f + 1); ensureBlock(P, f, f + 1); if (P.cfg.intr_opt == RCVD_INTR_SHARED) { ensureBlock(P, f - 1, 0); ensureBlock(P, f, 0); ensureBlock(P, f + 1, 0); } } }
   if (P.cfg.position_reg > 0.0)
     for (int f = 0; f + 2 < P.N; ++f) { ensureBlock(P, f, f + 1); ensureBlock(P, f, f + 2); ensureBlock(P, f + 1, f + 2); }
 }
@@ -893,6 +973,22 @@ static double evaluate(Problem& P, bool wantG, bool wantH, double* costStatic = 
   };
   for (int f = 0; f < P.N; ++f) regulariserRows(P, f, P.jacMode, sink);
   positionRows(P, sink);
+  {
+    double J[3 * kMaxPT]; int cols[kMaxPT]; double r[3];
+    for (size_t t = 0; t < P.tripCenters.size(); ++t) for (int64_t ci = P.tripOffsets[t]; ci < P.tripOffsets[t + 1]; ++ci) {
+      const float* rec = &P.tripRecords[size_t(ci) * 10];
+      const double w = double(rec[9]), sw = std::sqrt(w);
+      const int Pn = evalTriplet(P, P.tripCenters[t], rec, wantG || wantH, r, J, cols);
+      cost += 0.5 * w * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+      if (!(wantG || wantH)) continue;
+      for (int i = 0; i < 3; ++i) { r[i] *= sw; for (int j = 0; j < Pn; ++j) { double& v = J[i * kMaxPT + j]; v = constCol[cols[j] % n] ? 0.0 : v * sw; } }
+      if (wantG) for (int j = 0; j < Pn; ++j) P.g[cols[j]] += J[j] * r[0] + J[kMaxPT + j] * r[1] + J[2 * kMaxPT + j] * r[2];
+      if (wantH) for (int a = 0; a < Pn; ++a) for (int b = 0; b <= a; ++b) {
+        const double v = J[a] * J[b] + J[kMaxPT + a] * J[kMaxPT + b] + J[2 * kMaxPT + a] * J[2 * kMaxPT + b];
+        if (v != 0.0) addH(P, cols[a], cols[b], v);
+      }
+    }
+  }
   return cost;
 }
 
@@ -915,6 +1011,11 @@ static void activeMask(const Problem& P, std::vector<uint8_t>& act) {
   auto sink = [&](Row& row) { for (int i = 0; i < row.n; ++i) act[row.col[i]] = 1; };
   for (int f = 0; f < P.N; ++f) regulariserRows(Pm, f, 0, sink);
   positionRows(Pm, sink);
+  for (size_t t = 0; t < P.tripCenters.size(); ++t) for (int64_t ci = P.tripOffsets[t]; ci < P.tripOffsets[t + 1]; ++ci) {
+    ObsData o[3]; for (int i = 0; i < 3; ++i) makeObs(c, &P.tripRecords[size_t(ci) * 10 + 3 * i], o[i]);
+    int tc[kMaxPT]; const int Pn = tripletCols(P, P.tripCenters[t], o, tc);
+    for (int j = 0; j < Pn; ++j) act[tc[j]] = 1;
+  }
   for (int i = 0; i < P.U(); ++i) if (isConstLocal(P, i % n)) act[i] = 0;
 }
 
@@ -1328,7 +1429,7 @@ ORC_API int32_t orc_problem_create(const rcvd_config* c, Problem** out) {
   if (!L.ok || c->num_frames <= 0) { orc::g_err = "unsupported configuration"; return RCVD_ERR_INVALID; }
   Problem* P = new Problem(); P->cfg = *c; P->L = L; P->N = c->num_frames;
   P->inRange.assign(P->N, 1); P->median.assign(P->N, 1.0); P->x.assign(size_t(P->N) * L.nf, 0.0);
-  P->offsets.assign(1, 0);
+  P->offsets.assign(1, 0); P->tripOffsets.assign(1, 0);
   orc::buildScaleLocs(*P);
   *out = P; return RCVD_OK;
 }
@@ -1343,6 +1444,19 @@ ORC_API int32_t orc_problem_set_frames(Problem* P, const uint8_t* inr, const dou
 ORC_API int32_t orc_problem_set_constraints(Problem* P, int32_t np, const int32_t* pf, const int64_t* off, const float* rec) {
   P->pairFrames.assign(pf, pf + 2 * size_t(np)); P->offsets.assign(off, off + np + 1);
   P->records.assign(rec, rec + size_t(off[np]) * 6); P->H.clear();
+  return RCVD_OK;
+}
+ORC_API int32_t orc_problem_set_triplets(Problem* P, int32_t nt, const int32_t* centers, const int64_t* off, const float* rec) {
+  P->tripCenters.assign(centers, centers + nt); P->tripOffsets.assign(off, off + nt + 1); P->tripRecords.assign(rec, rec + size_t(off[nt]) * 10); P->H.clear();
+  return RCVD_OK;
+}
+// residuals and dense Jacobian (Jet) of the smoothness blocks, unweighted: r[3*T], J[3*T][U]
+ORC_API int32_t orc_triplet_jacobian(Problem* P, double* r, double* J) {
+  const int U = P->U(); double Jb[3 * orc::kMaxPT]; int cols[orc::kMaxPT];
+  for (size_t t = 0; t < P->tripCenters.size(); ++t) for (int64_t ci = P->tripOffsets[t]; ci < P->tripOffsets[t + 1]; ++ci) {
+    const int Pn = orc::evalTriplet(*P, P->tripCenters[t], &P->tripRecords[size_t(ci) * 10], true, r + 3 * ci, Jb, cols);
+    if (J) for (int i = 0; i < 3; ++i) { double* row = J + size_t(3 * ci + i) * U; for (int j = 0; j < Pn; ++j) row[cols[j]] += Jb[i * orc::kMaxPT + j]; }
+  }
   return RCVD_OK;
 }
 ORC_API int32_t orc_problem_set_state(Problem* P, const double* x) { P->x.assign(x, x + P->U()); return RCVD_OK; }

@@ -26,7 +26,7 @@ class Config(C.Structure):
         ("intr_opt", C.c_int32), ("static_loss_type", C.c_int32), ("robust_type", C.c_int32),
         ("fix_poses", C.c_int32), ("fix_depth_xforms", C.c_int32), ("fix_spatial_xforms", C.c_int32),
         ("depth_lower_bound", C.c_int32), ("scale_grid_x", C.c_int32), ("scale_grid_y", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("smooth_loss_type", C.c_int32),
         ("aspect", C.c_double), ("fixed_vfocal", C.c_double), ("robustness", C.c_double),
         ("static_spatial_weight", C.c_double), ("static_depth_weight", C.c_double),
         ("scale_reg", C.c_double), ("depth_deform_reg", C.c_double), ("adaptive_deform", C.c_double),
@@ -77,7 +77,7 @@ def default_config(num_frames, aspect, **kw):
         depth_grid_x=0, depth_grid_y=0, spatial_type=SPATIAL_IDENTITY, spatial_grid_x=0, spatial_grid_y=0,
         intr_opt=INTR_PER_FRAME, static_loss_type=LOSS_REPRO_DISPARITY, robust_type=ROBUST_CAUCHY,
         fix_poses=0, fix_depth_xforms=0, fix_spatial_xforms=0, depth_lower_bound=0,
-        scale_grid_x=0, scale_grid_y=0, reserved0=0,
+        scale_grid_x=0, scale_grid_y=0, smooth_loss_type=0,
         aspect=aspect, fixed_vfocal=vfocal, robustness=0.5,
         static_spatial_weight=1.0, static_depth_weight=1.0, scale_reg=1.0,
         depth_deform_reg=0.1, adaptive_deform=0.0, spatial_deform_reg=1.0, focal_reg=1.0,

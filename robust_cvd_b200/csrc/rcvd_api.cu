@@ -181,6 +181,8 @@ struct rcvd_problem {
   std::vector<uint8_t> in_range; std::vector<double> median, adaptive;
   std::vector<int32_t> pair_frames; std::vector<int64_t> offsets; std::vector<float> records_h;
   std::vector<int32_t> struct_pairs;   // global frame-pair graph (multi-GPU); empty -> local pairs
+  std::vector<int32_t> trip_centers; std::vector<int64_t> trip_offsets; std::vector<float> trip_records;   // smoothness triplets
+  float* d_trip_records = nullptr; int32_t *d_trip_tile_center = nullptr, *d_trip_tile_count = nullptr; int64_t* d_trip_tile_begin = nullptr; int num_trip_tiles = 0;
   int first_frame = 0, last_frame = -1;
   // device problem data
   float* d_records = nullptr; int32_t *d_tile_pair = nullptr, *d_tile_count = nullptr, *d_pair_frames = nullptr, *d_blk_of = nullptr;
@@ -240,6 +242,7 @@ static DevProblem dev_problem(const rcvd_problem* p) {
   d.pair_frames = p->d_pair_frames; d.blk_of = p->d_blk_of; d.in_range = p->d_in_range; d.median = p->d_median;
   d.adaptive = p->adaptive.empty() ? nullptr : p->d_adaptive; d.scale_locs = p->d_scale_locs; d.num_scale_locs = p->nscale;
   d.rank = p->rank; d.nranks = p->nranks;
+  d.trip_records = p->d_trip_records; d.trip_tile_center = p->d_trip_tile_center; d.trip_tile_begin = p->d_trip_tile_begin; d.trip_tile_count = p->d_trip_tile_count; d.num_trip_tiles = p->num_trip_tiles;
   return d;
 }
 
@@ -259,6 +262,12 @@ static int build_structure(rcvd_problem* p) {
     if (p->cfg.intr_opt == RCVD_INTR_SHARED) { addEdge(a, 0); addEdge(b, 0); }
   }
   if (p->cfg.position_reg > 0.0) for (int f = 0; f + 2 < N; ++f) { addEdge(f, f + 1); addEdge(f, f + 2); addEdge(f + 1, f + 2); }
+  for (size_t t = 0; t < p->trip_centers.size(); ++t) {
+    const int f = p->trip_centers[t];
+    if (f < 1 || f + 1 >= N) return set_err(RCVD_ERR_INVALID, "triplet centre frame out of range");
+    addEdge(f - 1, f); addEdge(f - 1, f + 1); addEdge(f, f + 1);
+    if (p->cfg.intr_opt == RCVD_INTR_SHARED) { addEdge(f - 1, 0); addEdge(f, 0); addEdge(f + 1, 0); }
+  }
   std::vector<std::set<int>> orig = adj;
   // Multiple minimum-degree elimination: each round eliminates a maximal independent set of frames whose current degree is
   // within `slack` of the minimum (ties -> lowest frame id).  slack = 0 is plain greedy minimum degree one frame at a time
@@ -366,6 +375,13 @@ static int build_structure(rcvd_problem* p) {
   p->num_tiles = (int)tile_pair.size(); p->C = p->offsets.empty() ? 0 : p->offsets.back();
   UP(p->d_tile_pair, tile_pair); UP(p->d_tile_begin, tile_begin); UP(p->d_tile_count, tile_count);
   UP(p->d_pair_frames, p->pair_frames); UP(p->d_records, p->records_h);
+  {
+    std::vector<int32_t> tc, tn; std::vector<int64_t> tb;
+    for (size_t i = 0; i < p->trip_centers.size(); ++i)
+      for (int64_t b = p->trip_offsets[i]; b < p->trip_offsets[i + 1]; b += kTile) { tc.push_back(p->trip_centers[i]); tb.push_back(b); tn.push_back((int32_t)std::min<int64_t>(kTile, p->trip_offsets[i + 1] - b)); }
+    p->num_trip_tiles = (int)tc.size();
+    UP(p->d_trip_tile_center, tc); UP(p->d_trip_tile_begin, tb); UP(p->d_trip_tile_count, tn); UP(p->d_trip_records, p->trip_records);
+  }
   UP(p->d_in_range, p->in_range); UP(p->d_median, p->median);
   if (!p->adaptive.empty()) UP(p->d_adaptive, p->adaptive);
   {
@@ -390,7 +406,7 @@ static int build_structure(rcvd_problem* p) {
   DA(p->d_g2, Upad + 8); DA(p->d_delta, Upad);
   DA(p->d_ytmp, Upad); DA(p->d_y, Upad); DA(p->d_Sy, Upad); DA(p->d_Hy, Upad); DA(p->d_scal, SC_N); DA(p->d_active, Upad); DA(p->d_fail, 1);
   const RegCounts rcn = reg_counts(p->cfg, L, N, p->nscale);
-  p->npartial = p->num_tiles + (rcn.total + 127) / 128 + 1;
+  p->npartial = p->num_tiles + (rcn.total + 127) / 128 + p->num_trip_tiles + 1;
   DA(p->d_partial, (size_t)p->npartial);
   DA(p->d_H, (size_t)p->nHblocks * bs); DA(p->d_Lb, (size_t)(N + nLoff) * bs); DA(p->d_T, (size_t)std::max(nLoff, 1) * bs);
   DA(p->d_invL, (size_t)N * bs); DA(p->d_invT, (size_t)N * npad * 16);
@@ -408,6 +424,7 @@ static int build_structure(rcvd_problem* p) {
     DevProblem d1 = d; d1.nranks = 1; d1.rank = 0;   // mark regardless of rank ownership
     k_regularisers<2><<<(rcn.total + 127) / 128, 128, 0, p->stream>>>(d1, rcn, p->d_x, nullptr, nullptr, nullptr, p->d_active, p->first_frame, p->last_frame);
   }
+  if (p->num_trip_tiles > 0) k_triplets<2><<<p->num_trip_tiles, kTile, 0, p->stream>>>(d, p->d_x, nullptr, nullptr, nullptr, p->d_active);
   k_finalize_mask<<<(int)((Upad + 255) / 256), 256, 0, p->stream>>>(p->cfg, L, p->d_active, N);
   CK(cudaGetLastError());
   // kernels that need > 48 KB dynamic smem
@@ -524,7 +541,14 @@ static int enqueue_evaluate(rcvd_problem* p, const double* x, bool wantG, bool w
     else k_regularisers<0><<<regblocks, 128, 0, st>>>(d, rcn, x, nullptr, nullptr, part, nullptr, p->first_frame, p->last_frame);
     p->launches++;
   }
-  k_reduce_partials<<<1, 1024, 0, st>>>(p->d_partial, p->num_tiles + regblocks, p->d_scal, slot);
+  if (p->num_trip_tiles > 0) {
+    double* part = p->d_partial + p->num_tiles + regblocks;
+    if (wantH) k_triplets<1><<<p->num_trip_tiles, kTile, 0, st>>>(d, x, p->d_H, gout, part, nullptr);
+    else if (wantG) k_triplets<3><<<p->num_trip_tiles, kTile, 0, st>>>(d, x, nullptr, gout, part, nullptr);
+    else k_triplets<0><<<p->num_trip_tiles, kTile, 0, st>>>(d, x, nullptr, nullptr, part, nullptr);
+    p->launches++;
+  }
+  k_reduce_partials<<<1, 1024, 0, st>>>(p->d_partial, p->num_tiles + regblocks + p->num_trip_tiles, p->d_scal, slot);
   p->launches++;
   CK(cudaGetLastError());
   if (p->nranks > 1) {
@@ -881,6 +905,18 @@ RCVD_API int32_t rcvd_problem_set_constraints(rcvd_problem* p, int32_t np, const
   const int64_t C = p->offsets.back();
   if (C > 0 && !rec) return set_err(RCVD_ERR_INVALID, "null records");
   p->records_h.assign(rec, rec + (size_t)C * 6);
+  p->structure_ready = false;
+  return RCVD_OK;
+}
+RCVD_API int32_t rcvd_problem_set_triplets(rcvd_problem* p, int32_t nt, const int32_t* centers, const int64_t* off, const float* rec) {
+  if (!p || nt < 0 || (nt > 0 && (!centers || !off))) return set_err(RCVD_ERR_INVALID, "bad triplet arrays");
+  if (p->structure_ready) { cudaSetDevice(p->device); cudaStreamSynchronize(p->stream); CK(cudaMemcpy(p->h_state.data(), p->d_x, p->h_state.size() * sizeof(double), cudaMemcpyDeviceToHost)); }
+  p->trip_centers.assign(centers, centers + nt);
+  if (nt > 0) p->trip_offsets.assign(off, off + nt + 1); else p->trip_offsets.assign(1, 0);
+  for (int i = 0; i < nt; ++i) if (p->trip_offsets[i + 1] < p->trip_offsets[i] || centers[i] < 1 || centers[i] + 1 >= p->N) return set_err(RCVD_ERR_INVALID, "bad triplet group %d", i);
+  const int64_t n = p->trip_offsets.back();
+  if (n > 0 && !rec) return set_err(RCVD_ERR_INVALID, "null triplet records");
+  p->trip_records.assign(rec, rec + (size_t)n * 10);
   p->structure_ready = false;
   return RCVD_OK;
 }

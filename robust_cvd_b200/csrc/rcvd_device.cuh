@@ -299,6 +299,110 @@ __device__ __forceinline__ void static_scene(const rcvd_config& c, const double*
   }
 }
 
+// worldToCamera (lib/PoseOptimizer.cpp:196-221) with derivatives: p = (x, y, depth); dpdX 3x3 (row-major),
+// dpdP 3x6 w.r.t. (t1, w1) of the receiving camera, dpdphi 3 w.r.t. its focal.
+template <bool JAC>
+__device__ __forceinline__ void world_to_camera(const double* pose1, double phi1, double a, const double X[3], double p[3],
+                                                double dpdX[9], double dpdP[18], double dpdphi[3]) {
+  const double rel[3] = {X[0] - pose1[0], X[1] - pose1[1], X[2] - pose1[2]};
+  const double v[3] = {-pose1[3], -pose1[4], -pose1[5]};
+  double q[3], R1[9], dq[9];
+  rotate_point<JAC>(v, rel, q, R1, dq);
+  const double depth = -q[2], id = 1.0 / depth, fx = phi1 * a, fy = phi1;
+  p[0] = q[0] * id / fx; p[1] = q[1] * id / fy; p[2] = depth;
+  if (JAC) {
+    const double g0[3] = {id / fx, 0.0, q[0] * id * id / fx}, g1[3] = {0.0, id / fy, q[1] * id * id / fy}, g2[3] = {0.0, 0.0, -1.0};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      dpdX[j] = g0[0] * R1[j] + g0[2] * R1[6 + j];
+      dpdX[3 + j] = g1[1] * R1[3 + j] + g1[2] * R1[6 + j];
+      dpdX[6 + j] = g2[2] * R1[6 + j];
+      dpdP[j] = -dpdX[j]; dpdP[6 + j] = -dpdX[3 + j]; dpdP[12 + j] = -dpdX[6 + j];
+      // dq/dw1 = -dq/dv
+      dpdP[3 + j] = -(g0[0] * dq[j] + g0[2] * dq[6 + j]);
+      dpdP[9 + j] = -(g1[1] * dq[3 + j] + g1[2] * dq[6 + j]);
+      dpdP[15 + j] = -(g2[2] * dq[6 + j]);
+    }
+    dpdphi[0] = -p[0] / phi1; dpdphi[1] = -p[1] / phi1; dpdphi[2] = 0.0;
+  }
+}
+
+// SceneFlowSmoothnessLoss (lib/PoseOptimizer.cpp:332-413) in local variables of the three frames:
+// r[3]; Jl[i*30 + j], j < 10 frame f-1, 10..19 frame f, 20..29 frame f+1 (t, w, phi, D, u per frame).
+template <bool JAC>
+__device__ __forceinline__ void smooth_scene(const rcvd_config& c, const double* const pose[3], const double phi[3], const double D[3],
+                                             const double (*u)[2], const ObsIn o[3], double r[3], double* Jl) {
+  const double a = c.aspect;
+  double X0[3], dX0[30], X2[3], dX2[30];
+  camera_to_world<JAC>(pose[0], phi[0], a, (double)o[0].ndcx + u[0][0], (double)o[0].ndcy + u[0][1], D[0], X0, dX0);
+  camera_to_world<JAC>(pose[2], phi[2], a, (double)o[2].ndcx + u[2][0], (double)o[2].ndcy + u[2][1], D[2], X2, dX2);
+  const double pc1x = (double)o[1].ndcx + u[1][0], pc1y = (double)o[1].ndcy + u[1][1];
+  if (JAC) {
+#pragma unroll
+    for (int i = 0; i < 90; ++i) Jl[i] = 0.0;
+  }
+  if (c.smooth_loss_type == RCVD_SMOOTH_EUCLIDEAN_LAPLACIAN) {   // :364-373
+    double X1[3], dX1[30];
+    camera_to_world<JAC>(pose[1], phi[1], a, pc1x, pc1y, D[1], X1, dX1);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      r[i] = X0[i] + X2[i] - 2.0 * X1[i];
+      if (JAC) {
+#pragma unroll
+        for (int j = 0; j < 10; ++j) { Jl[i * 30 + j] = dX0[i * 10 + j]; Jl[i * 30 + 10 + j] = -2.0 * dX1[i * 10 + j]; Jl[i * 30 + 20 + j] = dX2[i * 10 + j]; }
+      }
+    }
+    return;
+  }
+  double p01[3], p21[3], A0[9], A2[9], B0[18], B2[18], f0[3], f2[3];
+  world_to_camera<JAC>(pose[1], phi[1], a, X0, p01, A0, B0, f0);
+  world_to_camera<JAC>(pose[1], phi[1], a, X2, p21, A2, B2, f2);
+  const double ip = 1.0 / phi[1];
+  r[0] = (p01[0] + p21[0] - 2.0 * pc1x) * ip;
+  r[1] = (p01[1] + p21[1] - 2.0 * pc1y) * ip;
+  const double za = p01[2], zc = p21[2], zb = D[1];
+  double da, dc, db;   // d r2 / d(za, zc, zb)
+  if (c.smooth_loss_type == RCVD_SMOOTH_REPRO_DISPARITY_LAPLACIAN) {   // :388-394
+    const double eps = 1e-6;
+    const bool ca = za < eps, cb = zb < eps, cc = zc < eps;
+    r[2] = 1.0 / (ca ? eps : za) + 1.0 / (cc ? eps : zc) - 2.0 / (cb ? eps : zb);
+    da = ca ? 0.0 : -1.0 / (za * za); dc = cc ? 0.0 : -1.0 / (zc * zc); db = cb ? 0.0 : 2.0 / (zb * zb);
+  } else {   // :396-405: base = zb, other = za + zc - zb; max = (base<other)?other:base, min = (other<base)?other:base
+    const double base = zb, other = za + zc - zb;
+    const bool mxO = base < other, mnO = other < base;
+    const double mx = mxO ? other : base, mn = mnO ? other : base;
+    double dbase, dother;
+    if (c.smooth_loss_type == RCVD_SMOOTH_REPRO_DEPTH_RATIO_CONSISTENCY) {
+      r[2] = mx / mn - 1.0;
+      dbase = (mxO ? 0.0 : 1.0) / mn - mx / (mn * mn) * (mnO ? 0.0 : 1.0);
+      dother = (mxO ? 1.0 : 0.0) / mn - mx / (mn * mn) * (mnO ? 1.0 : 0.0);
+    } else {
+      r[2] = log(mn / mx);
+      dbase = (mnO ? 0.0 : 1.0) / mn - (mxO ? 0.0 : 1.0) / mx;
+      dother = (mnO ? 1.0 : 0.0) / mn - (mxO ? 1.0 : 0.0) / mx;
+    }
+    da = dother; dc = dother; db = dbase - dother;
+  }
+  if (JAC) {
+    const double wr[3] = {ip, ip, 0.0};
+#pragma unroll
+    for (int row = 0; row < 3; ++row) {
+      const double s0 = (row < 2) ? wr[row] : da, s2 = (row < 2) ? wr[row] : dc;
+#pragma unroll
+      for (int j = 0; j < 10; ++j) {
+        Jl[row * 30 + j] = s0 * (A0[row * 3] * dX0[j] + A0[row * 3 + 1] * dX0[10 + j] + A0[row * 3 + 2] * dX0[20 + j]);
+        Jl[row * 30 + 20 + j] = s2 * (A2[row * 3] * dX2[j] + A2[row * 3 + 1] * dX2[10 + j] + A2[row * 3 + 2] * dX2[20 + j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 6; ++j) Jl[row * 30 + 10 + j] = s0 * B0[row * 6 + j] + s2 * B2[row * 6 + j];
+    }
+    Jl[16] = (f0[0] + f2[0]) * ip - r[0] * ip;
+    Jl[30 + 16] = (f0[1] + f2[1]) * ip - r[1] * ip;
+    Jl[18] = -2.0 * ip; Jl[30 + 19] = -2.0 * ip;
+    Jl[60 + 17] = db;
+  }
+}
+
 // Robust loss rho(s) = {rho, rho', rho''}; CauchyLoss is the reference's
 // (lib/PoseOptimizer.cpp:1219-1220); restated from ceres/loss_function.cc.
 __device__ __forceinline__ void robust_loss(const rcvd_config& c, double s, double& rho0, double& rho1) {

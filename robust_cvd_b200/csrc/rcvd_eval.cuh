@@ -31,6 +31,8 @@ struct DevProblem {
   const float* scale_locs;     // [M][2]
   int num_scale_locs;
   int rank, nranks;            // regulariser rows are evaluated by rank f % nranks
+  // scene-flow smoothness triplets (optional): records [n][10], tiles of <= kTile constraints with one centre frame
+  const float* trip_records; const int32_t* trip_tile_center; const int64_t* trip_tile_begin; const int32_t* trip_tile_count; int num_trip_tiles;
 };
 
 __device__ __forceinline__ bool is_const_local(const rcvd_config& c, const Layout& L, int l) {
@@ -470,6 +472,85 @@ __global__ void __launch_bounds__(128) k_regularisers(DevProblem p, RegCounts rc
     }
   }
   if (MODE != 2) block_store_sum(cost, partial + blockIdx.x);
+}
+
+// --- scene-flow smoothness residual blocks (reference addSceneFlowSmoothnessLoss, lib/PoseOptimizer.cpp:1242-1339) ---
+// MODE 0: cost only, 1: cost + gradient + H, 2: mark active parameters, 3: cost + gradient
+template <int MODE>
+__global__ void __launch_bounds__(kTile) k_triplets(DevProblem p, const double* __restrict__ x, double* __restrict__ H, double* __restrict__ g,
+                                                    double* __restrict__ partial, uint8_t* __restrict__ mask) {
+  const rcvd_config& c = p.cfg; const Layout& L = p.L;
+  const int t = blockIdx.x;
+  const int fc = p.trip_tile_center[t];
+  const bool mine = (p.nranks <= 1) || (fc % p.nranks == p.rank) || MODE == 2;
+  double cost = 0.0;
+  if ((int)threadIdx.x < p.trip_tile_count[t] && mine) {
+    const float* rec = p.trip_records + (size_t)(p.trip_tile_begin[t] + threadIdx.x) * 10;
+    const int np = L.npad;
+    Gather dg[3], sg[3];
+    ObsIn o[3]; const double* pose[3]; double phi[3], D[3], u[3][2];
+    for (int i = 0; i < 3; ++i) {
+      o[i] = ObsIn{rec[3 * i], rec[3 * i + 1], rec[3 * i + 2]};
+      gather_depth(c, o[i].ndcx, o[i].ndcy, dg[i]); gather_spatial(c, o[i].ndcx, o[i].ndcy, sg[i]);
+      pose[i] = x + (size_t)(fc - 1 + i) * L.nf;
+    }
+    if (MODE == 2) {
+      for (int i = 0; i < 3; ++i) {
+        uint8_t* m = mask + (size_t)(fc - 1 + i) * np;
+        for (int q = 0; q < 6; ++q) m[q] = 1;
+        if (c.intr_opt == RCVD_INTR_PER_FRAME) m[6] = 1;
+        for (int q = 0; q < dg[i].n; ++q) for (int j = 0; j < L.k; ++j) m[L.offD + dg[i].idx[q] * L.k + j] = 1;
+        for (int q = 0; q < sg[i].n; ++q) { m[L.offS + sg[i].idx[q] * 2] = 1; m[L.offS + sg[i].idx[q] * 2 + 1] = 1; }
+      }
+      if (c.intr_opt == RCVD_INTR_SHARED) mask[6] = 1;
+      return;
+    }
+    for (int i = 0; i < 3; ++i) {
+      phi[i] = (c.intr_opt == RCVD_INTR_SHARED) ? x[6] : (c.intr_opt == RCVD_INTR_PER_FRAME ? pose[i][6] : c.fixed_vfocal);
+      D[i] = depth_value(c, L, dg[i], o[i].depth, pose[i]);
+      warp_value(L, sg[i], pose[i], u[i]);
+    }
+    const double w = (double)rec[9], sw = sqrt(w);   // ScaledLoss(nullptr, w): rho' = w
+    double r[3];
+    if (MODE == 0) {
+      smooth_scene<false>(c, pose, phi, D, u, o, r, nullptr);
+      cost = 0.5 * w * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+    } else {
+      double Jl[90];
+      smooth_scene<true>(c, pose, phi, D, u, o, r, Jl);
+      cost = 0.5 * w * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+      const double r0 = r[0] * sw, r1 = r[1] * sw, r2 = r[2] * sw;
+      int ef[kMaxEntries + 72]; short el[kMaxEntries + 72]; double ej[kMaxEntries + 72][3];
+      int E = 0;
+      auto push = [&](int f, int l, double a0, double a1, double a2) {
+        if (is_const_local(c, L, l)) return;
+        ef[E] = f; el[E] = (short)l; ej[E][0] = a0 * sw; ej[E][1] = a1 * sw; ej[E][2] = a2 * sw; ++E;
+      };
+      for (int side = 0; side < 3; ++side) {
+        const int f = fc - 1 + side, ofs = side * 10;
+        const double src = (double)o[side].depth;
+        for (int q = 0; q < 6; ++q) push(f, q, Jl[ofs + q], Jl[30 + ofs + q], Jl[60 + ofs + q]);
+        if (c.intr_opt == RCVD_INTR_PER_FRAME) push(f, 6, Jl[ofs + 6], Jl[30 + ofs + 6], Jl[60 + ofs + 6]);
+        for (int q = 0; q < dg[side].n; ++q) {
+          const double wq = dg[side].w[q];
+          push(f, L.offD + dg[side].idx[q] * L.k, Jl[ofs + 7] * wq * src, Jl[30 + ofs + 7] * wq * src, Jl[60 + ofs + 7] * wq * src);
+          if (L.k == 2) push(f, L.offD + dg[side].idx[q] * 2 + 1, Jl[ofs + 7] * wq, Jl[30 + ofs + 7] * wq, Jl[60 + ofs + 7] * wq);
+        }
+        for (int q = 0; q < sg[side].n; ++q) {
+          const double wq = sg[side].w[q];
+          push(f, L.offS + sg[side].idx[q] * 2, Jl[ofs + 8] * wq, Jl[30 + ofs + 8] * wq, Jl[60 + ofs + 8] * wq);
+          push(f, L.offS + sg[side].idx[q] * 2 + 1, Jl[ofs + 9] * wq, Jl[30 + ofs + 9] * wq, Jl[60 + ofs + 9] * wq);
+        }
+      }
+      if (c.intr_opt == RCVD_INTR_SHARED) push(0, 6, Jl[6] + Jl[16] + Jl[26], Jl[36] + Jl[46] + Jl[56], Jl[66] + Jl[76] + Jl[86]);
+      for (int a = 0; a < E; ++a) {
+        const double a0 = ej[a][0], a1 = ej[a][1], a2 = ej[a][2];
+        red_add(g + (size_t)ef[a] * np + el[a], a0 * r0 + a1 * r1 + a2 * r2);
+        if (MODE == 1) for (int b = 0; b <= a; ++b) add_h(p, H, ef[a], el[a], ef[b], el[b], a0 * ej[b][0] + a1 * ej[b][1] + a2 * ej[b][2]);
+      }
+    }
+  }
+  if (MODE != 2) block_store_sum(cost, partial + t);
 }
 
 // Final deterministic reduction of the per-block partial costs: out[slot] = sum(partial[0..n))

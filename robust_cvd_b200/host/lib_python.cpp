@@ -185,6 +185,9 @@ PYBIND11_MODULE(lib_python, m) {
         d["pair_frames"] = py::array_t<int32_t>(pa.pairFrames.size(), pa.pairFrames.data());
         d["offsets"] = py::array_t<int64_t>(pa.offsets.size(), pa.offsets.data());
         d["records"] = py::array_t<float>(pa.records.size(), pa.records.data());
+        d["trip_centers"] = py::array_t<int32_t>(pa.tripCenters.size(), pa.tripCenters.data());
+        d["trip_offsets"] = py::array_t<int64_t>(pa.tripOffsets.size(), pa.tripOffsets.data());
+        d["trip_records"] = py::array_t<float>(pa.tripRecords.size(), pa.tripRecords.data());
         return d; }, py::arg("params"), py::arg("constraints"), py::arg("depthDeformReg") = 0.1, py::arg("normalize") = false);
 
   py::class_<DepthVideoProcessor> dvp(m, "DepthVideoProcessor");

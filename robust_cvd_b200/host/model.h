@@ -302,6 +302,7 @@ class DepthVideoPoseOptimizer {
   struct ProblemArrays {
     rcvd_config cfg; std::vector<uint8_t> inRange; std::vector<double> median, adaptive, state;
     std::vector<int32_t> pairFrames; std::vector<int64_t> offsets; std::vector<float> records;
+    std::vector<int32_t> tripCenters; std::vector<int64_t> tripOffsets; std::vector<float> tripRecords;   // smoothness triplets, 10 floats each
     int pairCount = 0; int64_t constraintCount = 0;
   };
   ProblemArrays buildProblem(const Params& params, const FlowConstraintsCollection* constraints, double depthDeformReg, bool normalize);

@@ -45,8 +45,7 @@ DepthVideoPoseOptimizer::ProblemArrays DepthVideoPoseOptimizer::buildProblem(con
   int gx = params.scaleRegGridSize; int gy = int(std::round(float(gx) * video_->invAspect()));
   if (video_->aspect() <= 1.f) std::swap(gx, gy);
   cfg.scale_grid_x = gx; cfg.scale_grid_y = gy;
-  if ((params.smoothStaticWeight > 0.0 || params.smoothDynamicWeight > 0.0) && !normalize)
-    throw std::runtime_error("The scene-flow smoothness loss (smoothStaticWeight / smoothDynamicWeight > 0) is not implemented in this build.");
+  cfg.smooth_loss_type = int(params.smoothLossType);
   FrameRange range = params.frameRange;
   if (range.isEmpty()) range.resolve(numFrames_);
   pa.inRange.assign(numFrames_, 0);
@@ -130,6 +129,38 @@ DepthVideoPoseOptimizer::ProblemArrays DepthVideoPoseOptimizer::buildProblem(con
       pa.constraintCount += n;
     }
   }
+  // scene-flow smoothness constraints (addSceneFlowSmoothnessLoss :1242-1339): only if either weight is positive (:899-901)
+  pa.tripOffsets.assign(1, 0);
+  if (!normalize && constraints && (params.smoothStaticWeight > 0.0 || params.smoothDynamicWeight > 0.0)) {
+    const float invAspect = video_->invAspect();
+    for (int frame = range.firstFrame(); frame < range.lastFrame() - 1; ++frame) {
+      if (!range.inRange(frame) || !range.inRange(frame + 1) || !range.inRange(frame + 2)) continue;
+      const int triplet = frame + 1;
+      auto it = constraints->triplets().find(triplet);
+      if (it == constraints->triplets().end()) throw std::runtime_error("Missing triplet constraints.");
+      const Image* dimg[3];
+      for (int o = 0; o < 3; ++o) { dimg[o] = ds.frame(frame + o).sourceDepth(); if (!dimg[o]) throw std::runtime_error("Missing depth image."); }
+      const size_t before = pa.tripRecords.size();
+      for (const TripletConstraint& c : it->second) {
+        float rec[10]; bool ok = true;
+        for (int o = 0; o < 3; ++o) {
+          const Image* d = dimg[o];
+          const float lx = c.loc[o][0], ly = c.loc[o][1];
+          rec[o * 3] = -1.f + 2.f * lx; rec[o * 3 + 1] = 1.f - 2.f * ly / invAspect;
+          int px = int(lx * d->cols), py = int(ly / invAspect * d->rows);
+          px = std::min(std::max(px, 0), d->cols - 1); py = std::min(std::max(py, 0), d->rows - 1);
+          const float sd = d->ptr<float>(py)[px];
+          rec[o * 3 + 2] = sd;
+          if (!std::isfinite(sd) || sd <= 0) ok = false;
+        }
+        if (!ok) continue;
+        rec[9] = float(c.isStatic ? params.smoothStaticWeight : params.smoothDynamicWeight);   // ScaledLoss weight (:1314-1317)
+        pa.tripRecords.insert(pa.tripRecords.end(), rec, rec + 10);
+      }
+      pa.tripCenters.push_back(triplet);
+      pa.tripOffsets.push_back(pa.tripOffsets.back() + int64_t(pa.tripRecords.size() - before) / 10);
+    }
+  }
   // state
   pa.state.assign(size_t(numFrames_) * stride, 0.0);
   for (int f = 0; f < numFrames_; ++f) {
@@ -149,6 +180,7 @@ void DepthVideoPoseOptimizer::solveAndWriteBack(ProblemArrays& pa, const Params&
   try {
     checkStatus(rcvd_problem_set_frames(p, pa.inRange.data(), pa.median.data(), pa.adaptive.empty() ? nullptr : pa.adaptive.data()));
     checkStatus(rcvd_problem_set_constraints(p, int(pa.pairFrames.size() / 2), pa.pairFrames.data(), pa.offsets.data(), pa.records.data()));
+    if (!pa.tripCenters.empty()) checkStatus(rcvd_problem_set_triplets(p, int(pa.tripCenters.size()), pa.tripCenters.data(), pa.tripOffsets.data(), pa.tripRecords.data()));
     checkStatus(rcvd_problem_set_state(p, pa.state.data()));
     rcvd_solve_options opt; rcvd_default_solve_options(&opt);
     opt.max_iterations = params.maxIterations; opt.verbose = 1;   // minimizer_progress_to_stdout = true (:957)

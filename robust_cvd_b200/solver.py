@@ -93,6 +93,13 @@ class Problem:
         self.num_constraints = int(rec.shape[0])
         _check(self.L.rcvd_problem_set_constraints(self.h, C.c_int32(pf.shape[0]), _p(pf, C.c_int32), _p(off, C.c_int64), _p(rec, C.c_float)))
 
+    def set_triplets(self, centers, offsets, records):
+        """Scene-flow smoothness constraints (addSceneFlowSmoothnessLoss): centers[T], offsets[T+1], records[n][10]."""
+        ce = np.ascontiguousarray(centers, np.int32); off = np.ascontiguousarray(offsets, np.int64)
+        rec = np.ascontiguousarray(records, np.float32).reshape(-1, 10)
+        assert off.shape[0] == ce.shape[0] + 1 and off[-1] == rec.shape[0]
+        _check(self.L.rcvd_problem_set_triplets(self.h, C.c_int32(ce.shape[0]), _p(ce, C.c_int32), _p(off, C.c_int64), _p(rec, C.c_float)))
+
     def set_structure(self, pair_frames):
         pf = np.ascontiguousarray(pair_frames, np.int32).reshape(-1, 2)
         _check(self.L.rcvd_problem_set_structure(self.h, C.c_int32(pf.shape[0]), _p(pf, C.c_int32)))

@@ -176,6 +176,37 @@ class Scene:
         return (np.asarray(pairs, np.int32).reshape(-1, 2), np.asarray(offs, np.int64),
                 np.concatenate(recs, axis=0) if recs else np.zeros((0, 6), np.float32))
 
+    def triplet_records(self, f, sep, rng, w_static=1.0, w_dynamic=0.5, dynamic_fraction=0.2):
+        """Scene-flow smoothness constraints centred on frame f (f-1, f, f+1), emulating the triplet sampler
+        (lib/FlowConstraints.cpp:467-550): records [n][10] = 3 x (ndc.xy, depth) + weight."""
+        w, h = self.w, self.h
+        cell = max(sep, 1) * 1.2 + 0.04
+        nx = max(int(w / cell), 1); ny = max(int(h / cell), 1)
+        gy, gx = np.mgrid[0:ny, 0:nx]
+        ix = np.clip(np.floor((gx + 0.5) * (w / nx)).astype(int).ravel(), 0, w - 1); iy = np.clip(np.floor((gy + 0.5) * (h / ny)).astype(int).ravel(), 0, h - 1)
+        fx0, fy0, ok0 = self.flow(f, f - 1, ix, iy, rng); fx2, fy2, ok2 = self.flow(f, f + 1, ix, iy, rng)
+        ok = ok0 & ok2
+        for fx, fy in ((fx0, fy0), (fx2, fy2)):
+            ok &= (fx >= 0) & (fy >= 0) & ((fx + np.float32(0.5)).astype(np.int32) < w) & ((fy + np.float32(0.5)).astype(np.int32) < h)
+        ix, iy, fx0, fy0, fx2, fy2 = ix[ok], iy[ok], fx0[ok], fy0[ok], fx2[ok], fy2[ok]
+        sx = np.float32(1.0) / np.float32(w); sy = self.inv_aspect32 / np.float32(h)
+        rec = np.empty((ix.size, 10), np.float32)
+        for o, (frame, lx, ly) in enumerate(((f - 1, fx0 * sx, fy0 * sy), (f, ix.astype(np.float32) * sx, iy.astype(np.float32) * sy), (f + 1, fx2 * sx, fy2 * sy))):
+            rec[:, 3 * o] = np.float32(-1.0) + np.float32(2.0) * lx
+            rec[:, 3 * o + 1] = np.float32(1.0) - np.float32(2.0) * ly / self.inv_aspect32
+            px = np.clip((lx * np.float32(w)).astype(np.int32), 0, w - 1); py = np.clip((ly / self.inv_aspect32 * np.float32(h)).astype(np.int32), 0, h - 1)
+            rec[:, 3 * o + 2] = self.net_depth_at_pixel(frame, px, py)
+        rec[:, 9] = np.where(rng.uniform(size=ix.size) < dynamic_fraction, w_dynamic, w_static).astype(np.float32)
+        return rec
+
+    def triplets(self, sep=10, **kw):
+        rng = np.random.default_rng(self.seed + 4242)
+        centers, offs, recs = [], [0], []
+        for f in range(1, self.N - 1):
+            r = self.triplet_records(f, sep, rng, **kw)
+            centers.append(f); recs.append(r); offs.append(offs[-1] + r.shape[0])
+        return np.asarray(centers, np.int32), np.asarray(offs, np.int64), (np.concatenate(recs) if recs else np.zeros((0, 10), np.float32))
+
     def median_depths(self, stride=4):
         """Median over the emulated depth image (subsampled lattice keeps it cheap; a statistic only)."""
         out = np.zeros(self.N)

@@ -82,6 +82,39 @@ def test_fast_kernel_matches_generic(name):
     assert abs(cf - cg) <= 1e-12 * abs(cg)
 
 
+SMOOTH_CASES = [
+    (abi_smooth, ov) for abi_smooth, ov in [
+        (1, dict(depth_type=abi.DEPTH_GRID, depth_grid_x=4, depth_grid_y=4)),
+        (0, dict(depth_type=abi.DEPTH_GLOBAL, intr_opt=abi.INTR_SHARED)),
+        (2, dict(depth_type=abi.DEPTH_GRID, depth_cubic=1, depth_grid_x=4, depth_grid_y=3, spatial_type=abi.SPATIAL_BILINEAR_GRID, spatial_grid_x=3, spatial_grid_y=2)),
+        (3, dict(depth_type=abi.DEPTH_GLOBAL, intr_opt=abi.INTR_FIXED)),
+    ]]
+
+
+@pytest.mark.parametrize("smooth_type,overrides", SMOOTH_CASES, ids=["disparity_laplacian", "euclid_shared", "ratio_bicubic_warp", "log_fixed"])
+def test_scene_flow_smoothness_loss(smooth_type, overrides):
+    """SceneFlowSmoothnessLoss triplets (lib/PoseOptimizer.cpp:321-423, :1242-1339): CUDA analytic Jacobian vs the oracle's
+    literal Jet evaluation, and the LM result with the term enabled."""
+    from oracle import oracle
+    from robust_cvd_b200 import solver
+    sc, cfg, pairs, offs, rec, med = helpers.make_case(smooth_loss_type=smooth_type, **overrides)
+    ce, to, tr = sc.triplets(sep=14)
+    off_d, nd = helpers.layout_numbers(cfg)
+    O = oracle.OracleProblem(cfg); G = solver.Problem(cfg)
+    x = helpers.initial_state(sc, cfg, G.stride, off_d, nd)
+    for P in (O, G):
+        helpers.setup_problem(P, cfg, pairs, offs, rec, med, x); P.set_triplets(ce, to, tr)
+    co, go = O.evaluate(True); cg, gg = G.evaluate(True)
+    assert abs(co - cg) <= 1e-11 * abs(co)
+    assert np.abs(go - gg).max() <= 1e-9 * max(1.0, np.abs(go).max())
+    Ho, Hg = O.normal_matrix_dense(), G.normal_matrix_dense()
+    assert np.abs(Ho - Hg).max() <= 1e-9 * np.abs(Ho).max()
+    opt = abi.default_solve_options(max_iterations=25 if smooth_type == 0 else 50)
+    so, sg = O.solve(opt), G.solve(opt)
+    assert so.termination == sg.termination and abs(so.final_cost - sg.final_cost) <= 1e-6 * so.final_cost
+    assert np.linalg.norm(O.get_state() - G.get_state()) <= 1e-4 * np.linalg.norm(O.get_state())
+
+
 def test_normalize_depth_bounded():
     """normalizeDepth problem (lib/PoseOptimizer.cpp:992-1147): scale regulariser only, lower bound 0,
     Armijo line search along the projected path."""

@@ -24,6 +24,8 @@ def _oracle_replay(d, max_iterations):
     O = oracle.OracleProblem(cfg)
     O.set_frames(d["in_range"], d["median"], d["adaptive"] if d["adaptive"].size else None)
     O.set_constraints(d["pair_frames"].reshape(-1, 2), d["offsets"], d["records"].reshape(-1, 6))
+    if d["trip_centers"].size:
+        O.set_triplets(d["trip_centers"], d["trip_offsets"], d["trip_records"].reshape(-1, 10))
     O.set_state(d["state"])
     s = O.solve(abi.default_solve_options(max_iterations=max_iterations))
     return O.get_state(), s
@@ -89,6 +91,32 @@ def test_optimize_poses_sequence_matches_oracle_step_by_step(tmp_path):
     assert pm.shape == (96, 128) and pm.dtype == np.float64 and wp.shape == (96, 128, 2) and not wp.any()
     R = np.stack([f.extrinsics.right(), f.extrinsics.up(), f.extrinsics.backward()], 1)
     np.testing.assert_allclose(R.T @ R, np.eye(3), atol=1e-5)
+
+
+def test_smoothness_loss_through_lib_python(tmp_path):
+    """smoothStaticWeight / smoothDynamicWeight > 0 enables the scene-flow smoothness triplets (lib/PoseOptimizer.cpp:899-901)."""
+    import lib_python as lp
+    root = str(tmp_path / "scene")
+    sc = synthetic.Scene(8, 128, 96, seed=5)
+    synthetic_files.write_scene(sc, root)
+    v = lp.DepthVideo(); lp.DepthVideoImporter.importVideo(v, root, False)
+    v.createColorStream("down", "color_down", ".raw", CV_32FC3); v.createDepthStream("depth_midas2", "depth_midas2", [-1, -1])
+    fp = lp.FlowConstraintsParams(); fp.frameRange.resolve(v.numFrames(), True)
+    fc = lp.FlowConstraintsCollection(v, fp); fc.setStaticFlagFromDynamicMask(8)
+    proc = lp.DepthVideoProcessor(v)
+    params = lp.DepthVideoProcessor.Params(); params.depthStream = 0
+    params.poseOptimizer.frameRange.fromString("0-7"); params.poseOptimizer.maxIterations = 40
+    params.poseOptimizer.numSteps = 1; params.poseOptimizer.coarseToFine = False
+    params.poseOptimizer.smoothStaticWeight = 0.5; params.poseOptimizer.smoothDynamicWeight = 0.25
+    params.depthXformDesc.parse("Grid(Scale, Linear, 5, 4, 1)"); proc.resetDepthXforms(params)
+    opt = lp.DepthVideoPoseOptimizer(v, 0)
+    d = opt._buildProblem(params.poseOptimizer, fc, 0.1, False)
+    assert d["trip_centers"].tolist() == [1, 2, 3, 4, 5, 6] and d["trip_records"].size > 600
+    assert np.all(d["trip_records"].reshape(-1, 10)[:, 9] == np.float32(0.5))       # no dynamic masks -> all static
+    xo, so = _oracle_replay(d, 40)
+    proc.optimizePoses(params, fc)
+    xg = lp.DepthVideoPoseOptimizer(v, 0)._buildProblem(params.poseOptimizer, fc, 0.1, False)["state"].reshape(8, -1)
+    np.testing.assert_allclose(xg[:, 7:27], xo.reshape(8, -1)[:, 7:27], rtol=1e-4, atol=1e-7)
 
 
 def test_full_pose_optimization_call(tmp_path):

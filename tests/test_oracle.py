@@ -126,6 +126,29 @@ def test_normalize_depth_reaches_inverse_median():
     np.testing.assert_allclose(O.get_state()[:, 7], 1.0 / med, rtol=1e-6)
 
 
+@pytest.mark.parametrize("smooth_type", [0, 1, 2, 3])
+def test_smoothness_triplets_gradient(smooth_type):
+    from oracle import oracle
+    sc, cfg, pairs, offs, rec, med = helpers.make_case(smooth_loss_type=smooth_type, depth_type=abi.DEPTH_GRID, depth_grid_x=4, depth_grid_y=4)
+    ce, to, tr = sc.triplets(sep=14)
+    O = oracle.OracleProblem(cfg)
+    x = helpers.initial_state(sc, cfg, O.stride, 7, 16)
+    helpers.setup_problem(O, cfg, pairs, offs, rec, med, x); O.set_triplets(ce, to, tr)
+    c, g = O.evaluate(True)
+    r, J = O.triplet_jacobian()
+    w = np.repeat(tr[:, 9].astype(np.float64), 3)
+    O2 = oracle.OracleProblem(cfg); helpers.setup_problem(O2, cfg, pairs, offs, rec, med, x)
+    c2, g2 = O2.evaluate(True)
+    assert abs((c - c2) - 0.5 * (w * r * r).sum()) <= 1e-10 * c          # ScaledLoss: 1/2 w |r|^2
+    np.testing.assert_allclose(g - g2, J.T @ (w * r), atol=1e-9)
+    xf = x.reshape(-1).copy(); rng = np.random.default_rng(0)
+    for i in rng.choice(np.nonzero(O.active_mask())[0], 8, replace=False):
+        h = 1e-6
+        xp = xf.copy(); xp[i] += h; O.set_state(xp); cp = O.evaluate()
+        xm = xf.copy(); xm[i] -= h; O.set_state(xm); cm = O.evaluate()
+        assert abs((cp - cm) / (2 * h) - g[i]) <= 2e-5 * max(1.0, abs(g[i]))
+
+
 def test_hierarchical2_pairs_match_reference_golden():
     """tests/golden/hierarchical2_pairs.json was generated by importing the reference's
     utils/frame_sampling.py (tests/golden/make_golden.py)."""
