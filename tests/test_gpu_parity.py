@@ -139,3 +139,75 @@ def test_no_cpu_fallback_symbol():
     from robust_cvd_b200 import solver
     L = solver.lib()
     assert L.rcvd_abi_version() == 1
+
+
+def test_large_grid_uses_global_factor_kernel():
+    """npad > 224 takes the non-shared-memory potrf path (config 4's 32x24 grid is npad 784)."""
+    from oracle import oracle
+    from robust_cvd_b200 import solver
+    sc, cfg, pairs, offs, rec, med = helpers.make_case(num_frames=5, sep=6, depth_type=abi.DEPTH_GRID, depth_grid_x=20, depth_grid_y=14)
+    O = oracle.OracleProblem(cfg); G = solver.Problem(cfg)
+    assert G.stride == 287
+    x = helpers.initial_state(sc, cfg, G.stride, 7, 280)
+    helpers.setup_problem(O, cfg, pairs, offs, rec, med, x); helpers.setup_problem(G, cfg, pairs, offs, rec, med, x)
+    assert G.structure_info()["npad"] == 288
+    co, go = O.evaluate(True); cg, gg = G.evaluate(True)
+    assert abs(co - cg) <= 1e-11 * abs(co) and np.abs(go - gg).max() <= 1e-9 * max(1.0, np.abs(go).max())
+    opt = abi.default_solve_options(max_iterations=30)
+    so, sg = O.solve(opt), G.solve(opt)
+    assert so.termination == sg.termination and abs(so.final_cost - sg.final_cost) <= 1e-6 * so.final_cost
+    assert np.linalg.norm(O.get_state() - G.get_state()) <= 1e-4 * np.linalg.norm(O.get_state())
+
+
+def test_ragged_and_empty_inputs():
+    """Edge cases of BASELINE config 5 (holes: ~50 % valid pixels): ragged pair sizes, pairs without any constraint,
+    frames outside the range, a frame that no constraint touches."""
+    from oracle import oracle
+    from robust_cvd_b200 import solver, synthetic
+    sc = synthetic.Scene(8, 128, 96, seed=9)
+    cfg = abi.default_config(8, sc.aspect, depth_type=abi.DEPTH_GRID, depth_grid_x=4, depth_grid_y=4)
+    pairs, offs, rec = sc.constraints(sep=10, valid_fraction=0.5)
+    # drop every constraint of three pairs and of everything touching frame 7; keep the (now empty) pairs in the list
+    keep = np.ones(rec.shape[0], bool)
+    for p, (a, b) in enumerate(pairs):
+        if p in (0, 5, 11) or a == 7 or b == 7:
+            keep[offs[p]:offs[p + 1]] = False
+        elif p % 4 == 1:                      # ragged: thin some pairs to a handful of constraints
+            keep[offs[p] + 3:offs[p + 1]] = False
+    counts = np.array([keep[offs[p]:offs[p + 1]].sum() for p in range(len(pairs))]); rec = rec[keep]; offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    assert (counts == 0).sum() >= 5 and counts.max() > 2 * counts[counts > 0].min()
+    in_range = np.array([1, 1, 1, 1, 1, 1, 0, 1], np.uint8)       # frame 6 out of range (its pairs are simply not passed by the host)
+    sel = np.array([i for i, (a, b) in enumerate(pairs) if a != 6 and b != 6])
+    from robust_cvd_b200 import sharding
+    pairs2, offs2, rec2 = sharding.take_pairs(pairs, offs, rec, sel)
+    med = sc.median_depths()
+    res = []
+    for cls in (oracle.OracleProblem, solver.Problem):
+        P = cls(cfg)
+        P.set_frames(in_range, med); P.set_constraints(pairs2, offs2, rec2)
+        P.set_state(helpers.initial_state(sc, cfg, P.stride, 7, 16))
+        c, g = P.evaluate(True)
+        s = P.solve(abi.default_solve_options(max_iterations=40))
+        res.append((c, g, s.final_cost, s.termination, P.get_state()))
+    assert abs(res[0][0] - res[1][0]) <= 1e-11 * abs(res[0][0])
+    assert np.abs(res[0][1] - res[1][1]).max() <= 1e-9 * max(1.0, np.abs(res[0][1]).max())
+    assert res[0][3] == res[1][3] and abs(res[0][2] - res[1][2]) <= 1e-6 * res[0][2]
+    np.testing.assert_allclose(res[1][4], res[0][4], rtol=1e-4, atol=1e-9)
+    x0 = helpers.initial_state(sc, cfg, 23, 7, 16)
+    np.testing.assert_array_equal(res[1][4][6], x0[6])               # out-of-range frame untouched
+    np.testing.assert_array_equal(res[1][4][7][:6], x0[7][:6])       # pose of the unconstrained frame is not in the problem
+
+
+def test_dense_constraints_small():
+    """matchSeparation = 0 (every valid pixel): 0.3 M constraints on 8 frames, fast kernel vs oracle."""
+    from oracle import oracle
+    from robust_cvd_b200 import solver
+    sc, cfg, pairs, offs, rec, med = helpers.make_case(num_frames=4, sep=0, depth_type=abi.DEPTH_GRID, depth_grid_x=6, depth_grid_y=4)
+    assert rec.shape[0] > 100000
+    O = oracle.OracleProblem(cfg); G = solver.Problem(cfg)
+    x = helpers.initial_state(sc, cfg, G.stride, 7, 24)
+    helpers.setup_problem(O, cfg, pairs, offs, rec, med, x); helpers.setup_problem(G, cfg, pairs, offs, rec, med, x)
+    co, go = O.evaluate(True); cg, gg = G.evaluate(True)
+    assert abs(co - cg) <= 1e-10 * abs(co) and np.abs(go - gg).max() <= 1e-8 * max(1.0, np.abs(go).max())
+    Ho, Hg = O.normal_matrix_dense(), G.normal_matrix_dense()
+    assert np.abs(Ho - Hg).max() <= 1e-9 * np.abs(Ho).max()
