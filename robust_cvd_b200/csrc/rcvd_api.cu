@@ -201,13 +201,13 @@ struct rcvd_problem {
   std::vector<HBlock> hblocks;
   // schedule
   std::vector<Level> levels; int *d_lvl_frames = nullptr; GemmTask *d_trsm_tasks = nullptr, *d_upd_tasks = nullptr; int2 *d_trsm_pairs = nullptr, *d_upd_pairs = nullptr;
-  SolveTask *d_fwd_tasks = nullptr, *d_col_tasks = nullptr; int* d_col_ptr = nullptr;
+  SolveTask *d_fwd_tasks = nullptr, *d_col_tasks = nullptr; int* d_col_ptr = nullptr; TrsmTask* d_trsm_ll = nullptr; bool use_trsm_ll = false;
   cudaGraphExec_t solve_graph = nullptr;
   bool structure_ready = false, constraints_set = false, frames_set = false;
   // multi GPU
   int nranks = 1, rank = 0; nccl::Comm comm = nullptr;
   int64_t launches = 0, graph_launches = 0;
-  std::vector<double> h_state; bool state_dirty = false; bool use_fast = true; bool overlap = true; int order_slack = 3;   // multiple elimination with degree slack 3 (measured best at config 2); -1: greedy minimum degree
+  std::vector<double> h_state; bool state_dirty = false; bool use_fast = true; bool overlap = true; bool allow_trsm_ll = true; bool sub_solves = false; int order_slack = 3;   // multiple elimination with degree slack 3 (measured best at config 2); -1: greedy minimum degree
   cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   double *d_g2 = nullptr, *d_delta = nullptr; int* h_fail = nullptr;
   cudaEvent_t ev[8] = {nullptr};
@@ -323,7 +323,7 @@ static int build_structure(rcvd_problem* p) {
   std::vector<std::vector<int>> lf(nl);
   for (int k : order) lf[lvl[k]].push_back(k);
   std::vector<int> lvl_frames; std::vector<GemmTask> trsm_tasks, upd_tasks; std::vector<int2> trsm_pairs, upd_pairs;
-  std::vector<SolveTask> fwd_tasks, col_tasks; std::vector<int> col_ptr(N + 1, 0);
+  std::vector<SolveTask> fwd_tasks, col_tasks; std::vector<int> col_ptr(N + 1, 0); std::vector<TrsmTask> trsm_ll;
   p->levels.clear();
   for (int l = 0; l < nl; ++l) {
     Level lv; lv.frame_off = (int)lvl_frames.size(); lv.nframes = (int)lf[l].size();
@@ -335,6 +335,7 @@ static int build_structure(rcvd_problem* p) {
         const int id = lid[{r, k}];
         trsm_tasks.push_back({id - N, (int)trsm_pairs.size(), 1, 2});
         trsm_pairs.push_back(make_int2(id, k));
+        trsm_ll.push_back({id - N, id, k});
         fwd_tasks.push_back({id - N, r, k});
       }
       for (size_t a = 0; a < cs[k].size(); ++a) for (size_t b = 0; b <= a; ++b) {
@@ -366,7 +367,7 @@ static int build_structure(rcvd_problem* p) {
 #define UP(ptr, vec) if ((rc = upload(p, &(ptr), vec))) return rc
   UP(p->d_blk_of, blk_of); UP(p->d_hblocks, p->hblocks); UP(p->d_lblocks, lblocks); UP(p->d_lvl_frames, lvl_frames);
   UP(p->d_trsm_tasks, trsm_tasks); UP(p->d_upd_tasks, upd_tasks); UP(p->d_trsm_pairs, trsm_pairs); UP(p->d_upd_pairs, upd_pairs);
-  UP(p->d_fwd_tasks, fwd_tasks); UP(p->d_col_tasks, col_tasks); UP(p->d_col_ptr, col_ptr);
+  UP(p->d_fwd_tasks, fwd_tasks); UP(p->d_col_tasks, col_tasks); UP(p->d_col_ptr, col_ptr); UP(p->d_trsm_ll, trsm_ll);
   // tiles
   const int np = (int)(p->pair_frames.size() / 2);
   std::vector<int32_t> tile_pair, tile_count; std::vector<int64_t> tile_begin;
@@ -433,6 +434,8 @@ static int build_structure(rcvd_problem* p) {
   CK(cudaFuncSetAttribute(k_potrf, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
   CK(cudaFuncSetAttribute(k_trinv, cudaFuncAttributeMaxDynamicSharedMemorySize, (npad * 16 + 16 * (npad + 1)) * (int)sizeof(double)));
   CK(cudaFuncSetAttribute(k_accumulate_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem));
+  p->use_trsm_ll = p->allow_trsm_ll && trsm_ll_smem_bytes(npad) <= 220 * 1024;
+  if (p->use_trsm_ll) CK(cudaFuncSetAttribute(k_trsm_ll, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_ll_smem_bytes(npad)));
   if (potrf_smem_bytes(npad) <= 220 * 1024) CK(cudaFuncSetAttribute(k_potrf_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_smem_bytes(npad)));
   CK(cudaStreamSynchronize(p->stream));
   p->structure_ready = true;
@@ -449,16 +452,26 @@ static int enqueue_factor_solve(rcvd_problem* p) {
   // Two-stream schedule (fork/join inside the captured graph): the non-critical update GEMMs of level l run on `side`
   // concurrently with potrf / inverse / trsm of level l+1 on `st`.
   cudaStream_t side = p->side_stream;
-  bool side_pending = false;
+  bool side_pending = false, side_used = false;
   for (size_t li = 0; li < p->levels.size(); ++li) {
     const Level& lv = p->levels[li];
     if (potrf_smem_bytes(npad) <= 220 * 1024)
       k_potrf_smem<<<lv.nframes, kPotrfSmemThreads, potrf_smem_bytes(npad), st>>>(p->d_Lb, p->d_invT, p->d_lvl_frames + lv.frame_off, npad, p->d_fail);
     else
       k_potrf<<<lv.nframes, kPotrfThreads, npad * 17 * sizeof(double), st>>>(p->d_Lb, p->d_invT, p->d_lvl_frames + lv.frame_off, npad, p->d_fail);
-    k_trinv<<<dim3(npad / 16, lv.nframes), 256, (npad * 16 + 16 * (npad + 1)) * sizeof(double), st>>>(p->d_Lb, p->d_invT, p->d_invL, p->d_lvl_frames + lv.frame_off, npad);
-    p->launches += 2;
-    if (lv.ntrsm > 0) { k_gemm_nt<<<dim3(tiles, tiles, lv.ntrsm), 128, 0, st>>>(p->d_T, p->d_Lb, p->d_invL, p->d_trsm_tasks + lv.trsm_off, p->d_trsm_pairs, npad, 1.0, 0.0); p->launches++; }
+    p->launches += 1;
+    if (p->use_trsm_ll) {
+      // the explicit inverse is only needed by the (much later) substitution phase: compute it off the critical path
+      cudaStream_t is = st;
+      if (p->overlap) { CK(cudaEventRecord(p->ev_fork, st)); CK(cudaStreamWaitEvent(side, p->ev_fork, 0)); is = side; side_used = true; }
+      k_trinv<<<dim3(npad / 16, lv.nframes), 256, (npad * 16 + 16 * (npad + 1)) * sizeof(double), is>>>(p->d_Lb, p->d_invT, p->d_invL, p->d_lvl_frames + lv.frame_off, npad);
+      p->launches += 1;
+      if (lv.ntrsm > 0) { k_trsm_ll<<<dim3(tiles, lv.ntrsm), 128, trsm_ll_smem_bytes(npad), st>>>(p->d_T, p->d_Lb, p->d_invT, p->d_trsm_ll + lv.trsm_off, npad); p->launches++; }
+    } else {
+      k_trinv<<<dim3(npad / 16, lv.nframes), 256, (npad * 16 + 16 * (npad + 1)) * sizeof(double), st>>>(p->d_Lb, p->d_invT, p->d_invL, p->d_lvl_frames + lv.frame_off, npad);
+      p->launches += 1;
+      if (lv.ntrsm > 0) { k_gemm_nt<<<dim3(tiles, tiles, lv.ntrsm), 128, 0, st>>>(p->d_T, p->d_Lb, p->d_invL, p->d_trsm_tasks + lv.trsm_off, p->d_trsm_pairs, npad, 1.0, 0.0); p->launches++; }
+    }
     if (lv.nupd2 > 0 && p->overlap) {
       CK(cudaEventRecord(p->ev_fork, st)); CK(cudaStreamWaitEvent(side, p->ev_fork, 0));
     }
@@ -467,20 +480,22 @@ static int enqueue_factor_solve(rcvd_problem* p) {
     if (lv.nupd2 > 0) {
       cudaStream_t us = p->overlap ? side : st;
       k_gemm_nt<<<dim3(tiles, tiles, lv.nupd2), 128, 0, us>>>(p->d_Lb, p->d_T, p->d_T, p->d_upd_tasks + lv.upd2_off, p->d_upd_pairs, npad, -1.0, 1.0); p->launches++;
-      if (p->overlap) { CK(cudaEventRecord(p->ev_join, side)); side_pending = true; }
+      if (p->overlap) { CK(cudaEventRecord(p->ev_join, side)); side_pending = true; side_used = true; }
     }
   }
-  if (side_pending) CK(cudaStreamWaitEvent(st, p->ev_join, 0));
+  if (side_pending || side_used) { CK(cudaEventRecord(p->ev_join, side)); CK(cudaStreamWaitEvent(st, p->ev_join, 0)); }
   CK(cudaMemcpyAsync(p->d_rhs, p->d_gs, (size_t)N * npad * sizeof(double), cudaMemcpyDeviceToDevice, st));
   for (const Level& lv : p->levels) {
-    k_fwd_diag<<<dim3((npad + 7) / 8, lv.nframes), 256, 0, st>>>(p->d_invL, p->d_rhs, p->d_ytmp, p->d_lvl_frames + lv.frame_off, npad);
+    if (p->use_trsm_ll && p->sub_solves) k_fwd_diag_sub<<<lv.nframes, 256, (npad + 16) * sizeof(double), st>>>(p->d_Lb, p->d_invT, p->d_rhs, p->d_ytmp, p->d_lvl_frames + lv.frame_off, npad);
+    else k_fwd_diag<<<dim3((npad + 7) / 8, lv.nframes), 256, 0, st>>>(p->d_invL, p->d_rhs, p->d_ytmp, p->d_lvl_frames + lv.frame_off, npad);
     p->launches++;
     if (lv.nfwd > 0) { k_fwd_update<<<dim3((npad + 7) / 8, lv.nfwd), 256, 0, st>>>(p->d_T, p->d_ytmp, p->d_rhs, p->d_fwd_tasks + lv.fwd_off, npad); p->launches++; }
   }
   for (int l = (int)p->levels.size() - 1; l >= 0; --l) {
     const Level& lv = p->levels[l];
     if (lv.nfwd > 0) { k_bwd_update<<<dim3((npad + 31) / 32, lv.nfwd), 256, 0, st>>>(p->d_T, p->d_y, p->d_ytmp, p->d_fwd_tasks + lv.fwd_off, npad); p->launches++; }
-    k_bwd_diag<<<dim3((npad + 31) / 32, lv.nframes), 256, 0, st>>>(p->d_invL, p->d_ytmp, p->d_y, p->d_lvl_frames + lv.frame_off, npad);
+    if (p->use_trsm_ll && p->sub_solves) k_bwd_diag_sub<<<lv.nframes, 256, (npad + 16) * sizeof(double), st>>>(p->d_Lb, p->d_invT, p->d_ytmp, p->d_y, p->d_lvl_frames + lv.frame_off, npad);
+    else k_bwd_diag<<<dim3((npad + 31) / 32, lv.nframes), 256, 0, st>>>(p->d_invL, p->d_ytmp, p->d_y, p->d_lvl_frames + lv.frame_off, npad);
     p->launches += 1;
   }
   CK(cudaGetLastError());
@@ -1057,6 +1072,8 @@ RCVD_API int64_t rcvd_launch_count(rcvd_problem* p) { return p ? p->launches : 0
 RCVD_API int32_t rcvd_debug_set_order_slack(rcvd_problem* p, int32_t slack) { if (!p) return RCVD_ERR_INVALID; p->order_slack = slack; p->structure_ready = false; return RCVD_OK; }
 // Test / bench hook: 0 = single-stream factorisation graph, 1 (default) = overlap non-critical updates on a second stream.
 RCVD_API int32_t rcvd_debug_set_overlap(rcvd_problem* p, int32_t on) { if (!p) return RCVD_ERR_INVALID; p->overlap = on != 0; if (p->solve_graph) { cudaGraphExecDestroy(p->solve_graph); p->solve_graph = nullptr; } return RCVD_OK; }
+// Test / bench hook: 0 = explicit inverse + GEMM for the off-diagonal solves, 1 (default) = left-looking tensor-core TRSM.
+RCVD_API int32_t rcvd_debug_set_trsm_ll(rcvd_problem* p, int32_t on) { if (!p) return RCVD_ERR_INVALID; p->allow_trsm_ll = on != 0; p->structure_ready = false; return RCVD_OK; }
 RCVD_API int32_t rcvd_debug_set_fast_path(rcvd_problem* p, int32_t on) { if (!p) return RCVD_ERR_INVALID; p->use_fast = on != 0; return RCVD_OK; }
 RCVD_API int32_t rcvd_solve(rcvd_problem* p, const rcvd_solve_options* opt, rcvd_solve_summary* summary) {
   if (!p || !summary) return set_err(RCVD_ERR_INVALID, "null argument");

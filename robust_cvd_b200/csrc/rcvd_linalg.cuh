@@ -437,6 +437,160 @@ __global__ void __launch_bounds__(128, 4) k_gemm_nt(double* __restrict__ dst, co
 }
 
 // ---------------------------------------------------------------------------
+// k_trsm_ll: X_rk = A_rk * L_kk^{-T} by a left-looking tile recurrence on the fp64 tensor cores, needing only the 16x16
+// diagonal-tile inverses of k_potrf (no explicit inverse of L_kk):
+//     X[:, jt] = (A[:, jt] - sum_{pt<jt} X[:, pt] L[jt, pt]^T) * Di_jt^T          jt = 0 .. npad/16 - 1
+// One CTA = one 64-row strip of one block: 4 warps x 16 rows; the strip of X lives in shared memory
+// (64 x (npad+4) doubles), the L row panel of step jt is staged with cp.async one step ahead.
+// ---------------------------------------------------------------------------
+struct TrsmTask { int dst; int src; int kframe; };   // T index, L block id, column frame
+__host__ __device__ inline size_t trsm_ll_smem_bytes(int npad) { return ((size_t)64 * (npad + 4) + 2 * 16 * (size_t)(npad + 4) + 2 * 16 * 20) * sizeof(double); }
+
+__global__ void __launch_bounds__(128) k_trsm_ll(double* __restrict__ T, const double* __restrict__ Lb, const double* __restrict__ invT,
+                                                  const TrsmTask* __restrict__ tasks, int npad) {
+  extern __shared__ __align__(16) double smx[];
+  const int ld = npad + 4;                       // ld = 4 (mod 16): conflict-free DMMA fragment loads
+  double* Xs = smx;                              // [64][ld]
+  double* Ls = smx + (size_t)64 * ld;            // [2][16][ld]   L[jt*16 .. +15][0 .. jt*16)
+  double* Ds = Ls + (size_t)2 * 16 * ld;         // [2][16][20]   Di_jt
+  const TrsmTask task = tasks[blockIdx.y];
+  const int m0 = blockIdx.x * 64;
+  const size_t bs = (size_t)npad * npad;
+  const double* A = Lb + (size_t)task.src * bs;
+  const double* Lk = Lb + (size_t)task.kframe * bs;
+  const double* iT = invT + (size_t)task.kframe * npad * 16;
+  double* X = T + (size_t)task.dst * bs;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int nt = npad / 16;
+  const int rows = min(64, npad - m0);
+  // load the A strip (rows beyond the block are zero-filled)
+  for (int e = tid; e < 64 * (npad / 2); e += 128) {
+    const int r = e / (npad / 2), c = (e % (npad / 2)) * 2;
+    const bool v = r < rows;
+    cp_async16(&Xs[(size_t)r * ld + c], A + (size_t)(v ? m0 + r : 0) * npad + c, v);
+  }
+  auto stage = [&](int jt) {   // L row panel (columns [0, jt*16)) and Di of step jt into buffer jt & 1
+    double* ls = Ls + (size_t)(jt & 1) * 16 * ld; double* dsm = Ds + (jt & 1) * 320;
+    const int kw = jt * 16;
+    for (int e = tid; e < 16 * (kw / 2); e += 128) { const int r = e / (kw / 2), c = (e % (kw / 2)) * 2; cp_async16(&ls[(size_t)r * ld + c], Lk + (size_t)(jt * 16 + r) * npad + c, true); }
+    { const int r = tid >> 3, c = (tid & 7) * 2; cp_async16(&dsm[r * 20 + c], iT + (size_t)jt * 256 + r * 16 + c, true); }
+    cp_async_commit();
+  };
+  stage(0);
+  const int wr = warp * 16;                       // this warp's rows inside the strip
+  for (int jt = 0; jt < nt; ++jt) {
+    if (jt + 1 < nt) { stage(jt + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+    const double* ls = Ls + (size_t)(jt & 1) * 16 * ld; const double* dsm = Ds + (jt & 1) * 320;
+    double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+    for (int k4 = 0; k4 < jt * 4; ++k4) {
+      double af[2], bf[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) { af[i] = Xs[(size_t)(wr + i * 8 + g) * ld + k4 * 4 + t]; bf[i] = ls[(size_t)(i * 8 + g) * ld + k4 * 4 + t]; }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+    // Tt = A[:, jt] - acc, written back in place (each lane owns its C-fragment positions), then X[:, jt] = Tt * Di^T
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        double2* ptr = reinterpret_cast<double2*>(&Xs[(size_t)(wr + i * 8 + g) * ld + jt * 16 + j * 8 + 2 * t]);
+        double2 v = *ptr; v.x -= acc[i][j][0]; v.y -= acc[i][j][1]; *ptr = v;
+      }
+    __syncwarp();
+    double out[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+#pragma unroll
+    for (int k4 = 0; k4 < 4; ++k4) {
+      double af[2], bf[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) { af[i] = Xs[(size_t)(wr + i * 8 + g) * ld + jt * 16 + k4 * 4 + t]; bf[i] = dsm[(i * 8 + g) * 20 + k4 * 4 + t]; }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) dmma_8x8x4(out[i][j][0], out[i][j][1], af[i], bf[j]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int r = wr + i * 8 + g, cidx = jt * 16 + j * 8 + 2 * t;
+        const double2 v = make_double2(out[i][j][0], out[i][j][1]);
+        *reinterpret_cast<double2*>(&Xs[(size_t)r * ld + cidx]) = v;
+        if (r < rows) *reinterpret_cast<double2*>(&X[(size_t)(m0 + r) * npad + cidx]) = v;
+      }
+    __syncthreads();   // X[:, jt] visible to... (each warp only reads its own rows; the barrier protects the L/Di double buffer)
+  }
+}
+
+// Triangular solves with L_kk by 16-row tile substitution using the diagonal-tile inverses (no explicit inverse):
+//   forward  y_jt = Di_jt (b_jt - sum_{pt<jt} L[jt,pt] y_pt),   backward  x_jt = Di_jt^T (y_jt - sum_{pt>jt} L[pt,jt]^T x_pt)
+// one CTA (256 threads) per frame of the level; vectors are staged in shared memory.
+__global__ void __launch_bounds__(256) k_fwd_diag_sub(const double* __restrict__ Lb, const double* __restrict__ invT, const double* __restrict__ rhs,
+                                                       double* __restrict__ y, const int* __restrict__ frames, int npad) {
+  extern __shared__ double vs[];      // [npad] solution so far, [16] temp
+  double* tmp = vs + npad;
+  const int frame = frames[blockIdx.x];
+  const double* A = Lb + (size_t)frame * npad * npad; const double* iT = invT + (size_t)frame * npad * 16;
+  const double* b = rhs + (size_t)frame * npad;
+  const int tid = threadIdx.x, r = tid >> 4, c = tid & 15, nt = npad / 16;
+  for (int jt = 0; jt < nt; ++jt) {
+    // partial dot of row (jt*16 + r) over columns k = c, c+16, ... < jt*16
+    double s = 0.0;
+    const double* row = A + (size_t)(jt * 16 + r) * npad;
+    for (int k = c; k < jt * 16; k += 16) s += row[k] * vs[k];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);   // 16 lanes of a row are contiguous within the warp
+    if (c == 0) tmp[r] = b[jt * 16 + r] - s;
+    __syncthreads();
+    if (tid < 16) {
+      double acc = 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) acc += iT[(size_t)jt * 256 + tid * 16 + q] * tmp[q];
+      vs[jt * 16 + tid] = acc;
+      y[(size_t)frame * npad + jt * 16 + tid] = acc;
+    }
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(256) k_bwd_diag_sub(const double* __restrict__ Lb, const double* __restrict__ invT, const double* __restrict__ yin,
+                                                       double* __restrict__ x, const int* __restrict__ frames, int npad) {
+  extern __shared__ double vs[];
+  double* tmp = vs + npad;
+  const int frame = frames[blockIdx.x];
+  const double* A = Lb + (size_t)frame * npad * npad; const double* iT = invT + (size_t)frame * npad * 16;
+  const double* b = yin + (size_t)frame * npad;
+  const int tid = threadIdx.x, r = tid >> 4, c = tid & 15, nt = npad / 16;
+  for (int jt = nt - 1; jt >= 0; --jt) {
+    // column (jt*16 + c) of L below the tile, rows k = (jt+1)*16 + r, + 16, ...: sum_k L[k][jt*16+c] x_k
+    double s = 0.0;
+    for (int k = (jt + 1) * 16 + r; k < npad; k += 16) s += A[(size_t)k * npad + jt * 16 + c] * vs[k];
+    // reduce over r (stride 16 in tid): via shared memory
+    __shared__ double red[256];
+    red[tid] = s;
+    __syncthreads();
+    if (tid < 16) {
+      double acc = 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) acc += red[q * 16 + tid];
+      tmp[tid] = b[jt * 16 + tid] - acc;
+    }
+    __syncthreads();
+    if (tid < 16) {
+      double acc = 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) acc += iT[(size_t)jt * 256 + q * 16 + tid] * tmp[q];    // Di^T
+      vs[jt * 16 + tid] = acc;
+      x[(size_t)frame * npad + jt * 16 + tid] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Triangular solves as GEMVs with inv(L_kk); vectors have npad stride per frame.
 // ---------------------------------------------------------------------------
 // y_k = inv(L_kk) rhs_k   (grid: (ceil(npad/8), frames in level), 256 threads = 8 warps, one row per warp)
