@@ -218,8 +218,10 @@ struct rcvd_problem {
 template <class T> static int dalloc(rcvd_problem* p, T** ptr, size_t count) {
   *ptr = nullptr;
   if (count == 0) count = 1;
-  cudaError_t e = cudaMalloc((void**)ptr, count * sizeof(T));
-  if (e != cudaSuccess) return set_err(RCVD_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+  // stream-ordered pool allocation: the reference calls the solver once per schedule step, so a handle's
+  // gigabytes of factor storage are recycled from the pool instead of paying cudaMalloc/cudaFree per call
+  cudaError_t e = cudaMallocAsync((void**)ptr, count * sizeof(T), p->stream);
+  if (e != cudaSuccess) return set_err(RCVD_ERR_CUDA, "cudaMallocAsync(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
   p->allocs.push_back(*ptr);
   return RCVD_OK;
 }
@@ -230,8 +232,10 @@ template <class T> static int upload(rcvd_problem* p, T** ptr, const std::vector
 }
 static void free_all(rcvd_problem* p) {
   if (p->solve_graph) { cudaGraphExecDestroy(p->solve_graph); p->solve_graph = nullptr; }
-  for (void* q : p->allocs) cudaFree(q);
+  if (p->side_stream) cudaStreamSynchronize(p->side_stream);
+  for (void* q : p->allocs) cudaFreeAsync(q, p->stream);
   p->allocs.clear();
+  if (p->stream) cudaStreamSynchronize(p->stream);
   if (p->h_scal) { cudaFreeHost(p->h_scal); p->h_scal = nullptr; }
   p->structure_ready = false;
 }
@@ -877,6 +881,10 @@ RCVD_API int32_t rcvd_problem_create(const rcvd_config* cfg, int32_t device, rcv
   if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev)
     return set_err(RCVD_ERR_NO_DEVICE, "no usable CUDA device (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device ordinal out of range");
   CK(cudaSetDevice(device));
+  {  // keep freed blocks in the device's default pool (released only on cudaDeviceReset / explicit trim)
+    cudaMemPool_t pool; unsigned long long keep = ~0ull;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
   rcvd_problem* p = new rcvd_problem();
   p->cfg = *cfg; p->L = L; p->N = cfg->num_frames; p->device = device;
   e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
