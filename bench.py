@@ -37,6 +37,9 @@ WORKLOADS = {
     "config4_1000f_640x384_grid32x24_sep10": dict(frames=1000, w=640, h=384, gx=32, gy=24, sep=10),
 }
 METRIC = "flow_residual_constraints_per_sec_per_gn_iteration"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/), config 2;
+# None until a capture of the current kernel exists.
+NCU_TRAFFIC = {"gemm_nt": None, "accumulate": 149.1e6}
 
 
 def build_case(wl, frames=None, sep=None, seed=2, valid_fraction=1.0):
@@ -217,6 +220,8 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
     acc_ms = P.time_accumulate(iters=max(args.steps, 5))
+    lin_prof = P.profile_linear(reps=3)            # per-kernel-class device time, serialised (CUDA events around every launch)
+    peak64 = solver.fp64_tensor_peak(local)        # live DMMA peak (TFLOP/s) of this GPU
     # ---- e2e: C ABI with host buffers, copies inside the timed region ----
     e2e_iters = args.e2e_iters
     opt = abi.default_solve_options(max_iterations=e2e_iters)
@@ -258,9 +263,18 @@ def run_ours(args):
     # ids + 2 parameter vectors + the outputs (gradient + H blocks of the original structure)
     nf, npad = info["stride"], info["npad"]
     alg_bytes = 24.0 * C_total + len(pairs) * (8 + 16 * nf) + 8.0 * cfg.num_frames * nf + 8.0 * info["h_blocks"] * nf * nf
-    roof = {"bound": "hbm", "kernel": "gn_accumulate (k_accumulate_generic + k_regularisers)", "achieved": alg_bytes / (acc_ms * 1e-3) / 1e9,
-            "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / (acc_ms * 1e-3) / 1e9 / hbm_peak,
-            "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650 GB/s", "traffic": None, "ms": acc_ms}
+    roof_acc = {"bound": "hbm", "kernel": "gn_accumulate (k_accumulate_fast + k_regularisers)", "achieved": alg_bytes / (acc_ms * 1e-3) / 1e9,
+                "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / (acc_ms * 1e-3) / 1e9 / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650 GB/s",
+                "traffic": NCU_TRAFFIC.get("accumulate"), "ms": acc_ms,
+                "note": "fp64 Jacobian arithmetic bound, not HBM bound: see DESIGN.md section 5"}
+    # dominant kernel of the step: k_gemm_nt, the fp64 tensor-core block updates of the sparse Cholesky
+    n_g = max(lin_prof["gemm_launches"], 1.0)
+    g_tf = lin_prof["gemm_flops"] / max(lin_prof["gemm_ms"] * 1e-3, 1e-12) / 1e12
+    roof = {"bound": "tensor", "kernel": "k_gemm_nt (fp64 DMMA Schur updates of the block Cholesky)", "achieved": g_tf, "peak": peak64, "unit": "TFLOP/s",
+            "frac": g_tf / peak64, "peak_source": "fp64 DMMA.8x8x4 register loop measured live (rcvd_debug_fp64_tensor_peak); MEASURED_PEAKS.json has no fp64 figure",
+            "traffic": NCU_TRAFFIC.get("gemm_nt"), "launches_per_step": int(n_g), "avg_launch_us": lin_prof["gemm_ms"] * 1e3 / n_g,
+            "flops_per_launch": lin_prof["gemm_flops"] / n_g, "share_of_step_serialised": lin_prof["gemm_ms"] / max(sum(lin_prof[k] for k in ("load_ms", "potrf_ms", "trinv_ms", "trsm_ms", "gemm_ms", "solve_ms")) + acc_ms, 1e-9)}
     line = {"metric": METRIC, "value": C_total / (ms * 1e-3), "unit": "constraints/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload if not args.frames else f"{args.workload}[frames={args.frames}]", "frames": spec["frames"], "image": [spec["w"], spec["h"]],
@@ -268,7 +282,8 @@ def run_ours(args):
                        "unknowns": int(cfg.num_frames * nf), "parallelism": f"pair-sharded x{world}, replicated solve", "l2_note": "H/L working set >> L2 (126 MB)",
                        "structure": info},
             "breakdown_ms": {"accumulate": tm["accumulate_ms"], "factor_solve": tm["linear_ms"], "candidate_cost": tm["cost_ms"], "accumulate_isolated": acc_ms},
-            "roofline": roof, "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall}
+            "linear_kernels_ms_serialised": {k: lin_prof[k] for k in ("load_ms", "potrf_ms", "trinv_ms", "trsm_ms", "gemm_ms", "solve_ms")},
+            "roofline": roof, "roofline_accumulate": roof_acc, "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall}
     if e2e:
         line["e2e"] = e2e
     if world == 1 and not args.skip_cpu:

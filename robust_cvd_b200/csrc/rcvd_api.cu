@@ -212,6 +212,9 @@ struct rcvd_problem {
   double *d_g2 = nullptr, *d_delta = nullptr; int* h_fail = nullptr;
   cudaEvent_t ev[8] = {nullptr};
   std::vector<void*> allocs;
+  // kernel-class profiling (rcvd_debug_profile_linear): when set, enqueue_factor_solve records one event per launch
+  std::vector<std::pair<int, cudaEvent_t>>* prof = nullptr;
+  double upd_flops = 0.0;   // algorithmic flops of the update GEMMs of one factorisation (2 nf^3 per product, nf^2 (nf+1) on symmetric targets)
   rcvd_problem() {}
 };
 
@@ -326,6 +329,7 @@ static int build_structure(rcvd_problem* p) {
   for (int k : order) { for (int a : cs[k]) lvl[a] = std::max(lvl[a], lvl[k] + 1); nl = std::max(nl, lvl[k] + 1); }
   std::vector<std::vector<int>> lf(nl);
   for (int k : order) lf[lvl[k]].push_back(k);
+  double upd_flops = 0.0;
   std::vector<int> lvl_frames; std::vector<GemmTask> trsm_tasks, upd_tasks; std::vector<int2> trsm_pairs, upd_pairs;
   std::vector<SolveTask> fwd_tasks, col_tasks; std::vector<int> col_ptr(N + 1, 0); std::vector<TrsmTask> trsm_ll;
   p->levels.clear();
@@ -357,6 +361,7 @@ static int build_structure(rcvd_problem* p) {
         const bool critical = (lvl[cframe] == l + 1);
         if (critical != (pass == 0)) continue;
         upd_tasks.push_back({kv.first, (int)upd_pairs.size(), (int)kv.second.size(), kv.first < N ? 1 : 0});
+        { const double n = (double)L.nf; upd_flops += (double)kv.second.size() * (kv.first < N ? n * n * (n + 1.0) : 2.0 * n * n * n); }
         upd_pairs.insert(upd_pairs.end(), kv.second.begin(), kv.second.end());
       }
     }
@@ -369,6 +374,7 @@ static int build_structure(rcvd_problem* p) {
   // ---- device allocations ----
   int rc;
 #define UP(ptr, vec) if ((rc = upload(p, &(ptr), vec))) return rc
+  p->upd_flops = upd_flops;
   UP(p->d_blk_of, blk_of); UP(p->d_hblocks, p->hblocks); UP(p->d_lblocks, lblocks); UP(p->d_lvl_frames, lvl_frames);
   UP(p->d_trsm_tasks, trsm_tasks); UP(p->d_upd_tasks, upd_tasks); UP(p->d_trsm_pairs, trsm_pairs); UP(p->d_upd_pairs, upd_pairs);
   UP(p->d_fwd_tasks, fwd_tasks); UP(p->d_col_tasks, col_tasks); UP(p->d_col_ptr, col_ptr); UP(p->d_trsm_ll, trsm_ll);
@@ -451,8 +457,17 @@ static int enqueue_factor_solve(rcvd_problem* p) {
   const Layout& L = p->L; const int N = p->N, npad = L.npad; cudaStream_t st = p->stream;
   const int nL = N + p->nLoff;
   const int tiles = (npad + 63) / 64;
+  enum { P_LOAD = 0, P_POTRF, P_TRINV, P_TRSM, P_GEMM, P_SOLVE };
+  auto mark = [&](int cls) {   // profiling mode only (single stream, not captured)
+    if (!p->prof) return;
+    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); p->prof->push_back({cls, e});
+  };
+  auto gemm = [&](cudaStream_t cs, int ntasks, double* dstp, const double* A, const double* B, const GemmTask* tasks, const int2* prs, double alpha, double beta) {
+    k_gemm_nt<<<dim3(tiles, tiles, ntasks), 128, 0, cs>>>(dstp, A, B, tasks, prs, npad, alpha, beta);
+  };
+  mark(-1);
   k_load_factor<<<dim3((npad * npad + 255) / 256, nL), 256, 0, st>>>(p->d_H, p->d_Lb, p->d_lblocks, p->d_S, p->d_D2, npad, L.nf);
-  p->launches += 1;
+  p->launches += 1; mark(P_LOAD);
   // Two-stream schedule (fork/join inside the captured graph): the non-critical update GEMMs of level l run on `side`
   // concurrently with potrf / inverse / trsm of level l+1 on `st`.
   cudaStream_t side = p->side_stream;
@@ -463,27 +478,27 @@ static int enqueue_factor_solve(rcvd_problem* p) {
       k_potrf_smem<<<lv.nframes, kPotrfSmemThreads, potrf_smem_bytes(npad), st>>>(p->d_Lb, p->d_invT, p->d_lvl_frames + lv.frame_off, npad, p->d_fail);
     else
       k_potrf<<<lv.nframes, kPotrfThreads, npad * 17 * sizeof(double), st>>>(p->d_Lb, p->d_invT, p->d_lvl_frames + lv.frame_off, npad, p->d_fail);
-    p->launches += 1;
+    p->launches += 1; mark(P_POTRF);
     if (p->use_trsm_ll) {
       // the explicit inverse is only needed by the (much later) substitution phase: compute it off the critical path
       cudaStream_t is = st;
       if (p->overlap) { CK(cudaEventRecord(p->ev_fork, st)); CK(cudaStreamWaitEvent(side, p->ev_fork, 0)); is = side; side_used = true; }
       k_trinv<<<dim3(npad / 16, lv.nframes), 256, (npad * 16 + 16 * (npad + 1)) * sizeof(double), is>>>(p->d_Lb, p->d_invT, p->d_invL, p->d_lvl_frames + lv.frame_off, npad);
-      p->launches += 1;
-      if (lv.ntrsm > 0) { k_trsm_ll<<<dim3(tiles, lv.ntrsm), 128, trsm_ll_smem_bytes(npad), st>>>(p->d_T, p->d_Lb, p->d_invT, p->d_trsm_ll + lv.trsm_off, npad); p->launches++; }
+      p->launches += 1; mark(P_TRINV);
+      if (lv.ntrsm > 0) { k_trsm_ll<<<dim3(tiles, lv.ntrsm), 128, trsm_ll_smem_bytes(npad), st>>>(p->d_T, p->d_Lb, p->d_invT, p->d_trsm_ll + lv.trsm_off, npad); p->launches++; mark(P_TRSM); }
     } else {
       k_trinv<<<dim3(npad / 16, lv.nframes), 256, (npad * 16 + 16 * (npad + 1)) * sizeof(double), st>>>(p->d_Lb, p->d_invT, p->d_invL, p->d_lvl_frames + lv.frame_off, npad);
-      p->launches += 1;
-      if (lv.ntrsm > 0) { k_gemm_nt<<<dim3(tiles, tiles, lv.ntrsm), 128, 0, st>>>(p->d_T, p->d_Lb, p->d_invL, p->d_trsm_tasks + lv.trsm_off, p->d_trsm_pairs, npad, 1.0, 0.0); p->launches++; }
+      p->launches += 1; mark(P_TRINV);
+      if (lv.ntrsm > 0) { gemm(st, lv.ntrsm, p->d_T, p->d_Lb, p->d_invL, p->d_trsm_tasks + lv.trsm_off, p->d_trsm_pairs, 1.0, 0.0); p->launches++; mark(P_TRSM); }
     }
     if (lv.nupd2 > 0 && p->overlap) {
       CK(cudaEventRecord(p->ev_fork, st)); CK(cudaStreamWaitEvent(side, p->ev_fork, 0));
     }
     if (side_pending) { CK(cudaStreamWaitEvent(st, p->ev_join, 0)); side_pending = false; }   // U2(l-1) before U1(l)
-    if (lv.nupd > 0) { k_gemm_nt<<<dim3(tiles, tiles, lv.nupd), 128, 0, st>>>(p->d_Lb, p->d_T, p->d_T, p->d_upd_tasks + lv.upd_off, p->d_upd_pairs, npad, -1.0, 1.0); p->launches++; }
+    if (lv.nupd > 0) { gemm(st, lv.nupd, p->d_Lb, p->d_T, p->d_T, p->d_upd_tasks + lv.upd_off, p->d_upd_pairs, -1.0, 1.0); p->launches++; mark(P_GEMM); }
     if (lv.nupd2 > 0) {
       cudaStream_t us = p->overlap ? side : st;
-      k_gemm_nt<<<dim3(tiles, tiles, lv.nupd2), 128, 0, us>>>(p->d_Lb, p->d_T, p->d_T, p->d_upd_tasks + lv.upd2_off, p->d_upd_pairs, npad, -1.0, 1.0); p->launches++;
+      gemm(us, lv.nupd2, p->d_Lb, p->d_T, p->d_T, p->d_upd_tasks + lv.upd2_off, p->d_upd_pairs, -1.0, 1.0); p->launches++; mark(P_GEMM);
       if (p->overlap) { CK(cudaEventRecord(p->ev_join, side)); side_pending = true; side_used = true; }
     }
   }
@@ -502,6 +517,7 @@ static int enqueue_factor_solve(rcvd_problem* p) {
     else k_bwd_diag<<<dim3((npad + 31) / 32, lv.nframes), 256, 0, st>>>(p->d_invL, p->d_ytmp, p->d_y, p->d_lvl_frames + lv.frame_off, npad);
     p->launches += 1;
   }
+  mark(P_SOLVE);
   CK(cudaGetLastError());
   return RCVD_OK;
 }
@@ -1073,6 +1089,73 @@ RCVD_API int32_t rcvd_time_iteration(rcvd_problem* p, int32_t iters, double radi
   }
   *ms_iter = tt / iters; if (ms_acc) *ms_acc = ta / iters; if (ms_lin) *ms_lin = tl / iters; if (ms_cost) *ms_cost = tc / iters;
   return RCVD_OK;
+}
+// Bench hook: one factorisation + solve, un-captured on a single stream with one CUDA event per launch; returns the
+// summed device time per kernel class: out_ms[0..5] = load, potrf, trinv, trsm, update GEMM (k_gemm_nt), substitution;
+// out_ms[6] = number of k_gemm_nt update launches, out_ms[7] = algorithmic flops of those GEMMs.
+RCVD_API int32_t rcvd_debug_profile_linear(rcvd_problem* p, int32_t reps, double out_ms[8]) {
+  if (!p || !out_ms || reps <= 0) return set_err(RCVD_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(p->device));
+  int rc = ensure_ready(p); if (rc) return rc;
+  const bool ov = p->overlap; p->overlap = false;
+  for (int i = 0; i < 8; ++i) out_ms[i] = 0.0;
+  std::vector<std::pair<int, cudaEvent_t>> evs;
+  for (int r = -1; r < reps; ++r) {
+    CK(cudaMemsetAsync(p->d_fail, 0, sizeof(int), p->stream));
+    evs.clear(); p->prof = &evs;
+    rc = enqueue_factor_solve(p);
+    p->prof = nullptr;
+    cudaStreamSynchronize(p->stream);
+    double ngemm = 0;
+    for (size_t i = 1; i < evs.size(); ++i) {
+      float ms = 0; cudaEventElapsedTime(&ms, evs[i - 1].second, evs[i].second);
+      if (r >= 0 && evs[i].first >= 0 && evs[i].first < 6) out_ms[evs[i].first] += ms;
+      if (evs[i].first == 4) ngemm += 1;
+    }
+    for (auto& e : evs) cudaEventDestroy(e.second);
+    out_ms[6] = ngemm;
+    if (rc) break;
+  }
+  p->overlap = ov;
+  for (int i = 0; i < 6; ++i) out_ms[i] /= reps;
+  out_ms[7] = p->upd_flops;
+  return rc;
+}
+// Bench hook: fp64 tensor-core (DMMA m8n8k4) peak of this device, measured live with a register-only loop on all SMs.
+// MEASURED_PEAKS.json carries HBM and bf16 figures only; this is the denominator of the update-GEMM roofline.
+__global__ void k_dmma_peak(double* out, int iters) {
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { c[i][0] = 0; c[i][1] = 0; }
+  const double a = threadIdx.x * 1e-3, b = 1.0 + threadIdx.x * 1e-6;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dmma_8x8x4(c[i][0], c[i][1], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+RCVD_API int32_t rcvd_debug_fp64_tensor_peak(int32_t device, double* tflops) {
+  if (!tflops) return set_err(RCVD_ERR_INVALID, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return set_err(RCVD_ERR_NO_DEVICE, "no usable CUDA device");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
+  const int threads = 512, blocks = prop.multiProcessorCount * 4, iters = 20000;
+  double* out = nullptr; CK(cudaMalloc((void**)&out, (size_t)blocks * threads * sizeof(double)));
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0); k_dmma_peak<<<blocks, threads>>>(out, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    const double tf = 2.0 * 256 * 8 * iters * (double)blocks * (threads / 32) / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  CK(cudaGetLastError());
+  *tflops = best; return RCVD_OK;
 }
 RCVD_API int64_t rcvd_launch_count(rcvd_problem* p) { return p ? p->launches : 0; }
 // Test hook: 0 forces the generic accumulate kernel, 1 (default) allows the specialised one.

@@ -331,6 +331,9 @@ __global__ void __launch_bounds__(256) k_trinv(const double* __restrict__ Lb, co
 // fp64 tensor cores (mma.sync m8n8k4 -> DMMA), CTA tile 64x64, 4 warps of 32x32,
 // K staged 16 at a time through a cp.async double buffer.
 // ---------------------------------------------------------------------------
+// Measured alternatives that lost at npad = 208 (config 2, 91 update launches, 133.7 GFLOP algorithmic): 96x96 CTA tiles with
+// 3x3-unit warp tiles (250 registers, 2 CTAs/SM): 12.8 TFLOP/s; balanced <=64-row chunks (3,3,3,4 units): 16.1 TFLOP/s;
+// this kernel: 16.7 TFLOP/s.  The short last tile row is cheap because out-of-range mma tiles are never issued.
 struct GemmTask { int dst; int first; int count; int lower_only; };   // lower_only bit0: symmetric target (skip tiles above the diagonal); bit1: B is lower triangular
 
 constexpr int kGemmLd = 20;   // padded leading dimension of the 64x16 smem tiles (conflict-free DMMA fragment loads)

@@ -158,6 +158,13 @@ class Problem:
         keys = ["frames", "offdiag_factor_blocks", "levels", "h_blocks", "npad", "stride", "tiles", "update_tasks"]
         return dict(zip(keys, list(out)))
 
+    def profile_linear(self, reps=3):
+        """Bench hook: per-kernel-class device time of one factorisation + solve (serialised on one stream, CUDA events per launch)."""
+        out = (C.c_double * 8)()
+        _check(self.L.rcvd_debug_profile_linear(self.h, C.c_int32(reps), out))
+        keys = ["load_ms", "potrf_ms", "trinv_ms", "trsm_ms", "gemm_ms", "solve_ms", "gemm_launches", "gemm_flops"]
+        return dict(zip(keys, list(out)))
+
     def set_fast_path(self, on=True):
         """Test hook: False forces the generic accumulate kernel."""
         _check(self.L.rcvd_debug_set_fast_path(self.h, C.c_int32(1 if on else 0)))
@@ -202,3 +209,10 @@ def spatial_warp(cfg, spatial_params, h, w, device=0):
     sp = np.ascontiguousarray(spatial_params, np.float64); out = np.empty((h, w, 2), np.float32)
     _check(lib().rcvd_spatial_warp(C.byref(cfg), C.c_int32(device), _p(sp, C.c_double), _p(out, C.c_float), C.c_int32(h), C.c_int32(w)))
     return out
+
+
+def fp64_tensor_peak(device=0):
+    """Bench hook: live-measured fp64 tensor-core (DMMA) peak of `device` in TFLOP/s."""
+    v = C.c_double()
+    _check(lib().rcvd_debug_fp64_tensor_peak(C.c_int32(device), C.byref(v)))
+    return v.value

@@ -13,6 +13,7 @@ ap.add_argument("--iters", type=int, default=1)
 ap.add_argument("--accumulate-only", action="store_true")
 ap.add_argument("--slack", type=int, default=None)
 ap.add_argument("--no-overlap", action="store_true")
+ap.add_argument("--classes", action="store_true", help="also print the serialised per-kernel-class times")
 a = ap.parse_args()
 spec, sc, cfg, pairs, offs, rec, med = bench.build_case(a.workload, frames=a.frames, sep=a.sep)
 P = solver.Problem(cfg)
@@ -23,3 +24,7 @@ if a.accumulate_only:
     print("accumulate ms", P.time_accumulate(iters=a.iters))
 else:
     print(P.time_iteration(iters=a.iters), P.structure_info(), "C", rec.shape[0])
+    if a.classes:
+        pl = P.profile_linear(reps=3)
+        pl["gemm_tflops"] = pl["gemm_flops"] / (pl["gemm_ms"] * 1e-3) / 1e12
+        print({k: round(v, 3) if v < 1e6 else v for k, v in pl.items()})
