@@ -207,7 +207,7 @@ struct rcvd_problem {
   // multi GPU
   int nranks = 1, rank = 0; nccl::Comm comm = nullptr;
   int64_t launches = 0, graph_launches = 0;
-  std::vector<double> h_state; bool state_dirty = false; bool use_fast = true; bool overlap = true; bool allow_trsm_ll = true; bool sub_solves = false; int order_slack = 3;   // multiple elimination with degree slack 3 (measured best at config 2); -1: greedy minimum degree
+  std::vector<double> h_state; bool state_dirty = false; bool use_fast = true; bool overlap = true; int side_slice = 0; bool allow_trsm_ll = true; bool sub_solves = false; int order_slack = 3;   // multiple elimination with degree slack 3 (measured best at config 2); -1: greedy minimum degree
   cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   double *d_g2 = nullptr, *d_delta = nullptr; int* h_fail = nullptr;
   cudaEvent_t ev[8] = {nullptr};
@@ -498,7 +498,12 @@ static int enqueue_factor_solve(rcvd_problem* p) {
     if (lv.nupd > 0) { gemm(st, lv.nupd, p->d_Lb, p->d_T, p->d_T, p->d_upd_tasks + lv.upd_off, p->d_upd_pairs, -1.0, 1.0); p->launches++; mark(P_GEMM); }
     if (lv.nupd2 > 0) {
       cudaStream_t us = p->overlap ? side : st;
-      gemm(us, lv.nupd2, p->d_Lb, p->d_T, p->d_T, p->d_upd_tasks + lv.upd2_off, p->d_upd_pairs, -1.0, 1.0); p->launches++; mark(P_GEMM);
+      // sliced so that the grid of one launch is about `side_slice` CTAs: a potrf / trsm CTA of the chain needs most of an SM's
+      // shared memory and can only start on an SM that has drained, which a long low-priority grid never lets happen
+      const int per = (p->overlap && p->side_slice > 0) ? std::max(1, p->side_slice / (tiles * tiles)) : lv.nupd2;
+      for (int o = 0; o < lv.nupd2; o += per) {
+        gemm(us, std::min(per, lv.nupd2 - o), p->d_Lb, p->d_T, p->d_T, p->d_upd_tasks + lv.upd2_off + o, p->d_upd_pairs, -1.0, 1.0); p->launches++; mark(P_GEMM);
+      }
       if (p->overlap) { CK(cudaEventRecord(p->ev_join, side)); side_pending = true; side_used = true; }
     }
   }
@@ -903,8 +908,11 @@ RCVD_API int32_t rcvd_problem_create(const rcvd_config* cfg, int32_t device, rcv
   }
   rcvd_problem* p = new rcvd_problem();
   p->cfg = *cfg; p->L = L; p->N = cfg->num_frames; p->device = device;
-  e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->side_stream, cudaStreamNonBlocking);
+  // the critical chain (potrf -> trsm -> next-level updates) runs at the highest priority, the overlapped updates at the lowest,
+  // so that a freed SM goes to the chain first
+  int prio_lo = 0, prio_hi = 0; cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  e = cudaStreamCreateWithPriority(&p->stream, cudaStreamNonBlocking, prio_hi);
+  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&p->side_stream, cudaStreamNonBlocking, prio_lo);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming);
   if (e != cudaSuccess) { delete p; return set_err(RCVD_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
@@ -1093,11 +1101,14 @@ RCVD_API int32_t rcvd_time_iteration(rcvd_problem* p, int32_t iters, double radi
 // Bench hook: one factorisation + solve, un-captured on a single stream with one CUDA event per launch; returns the
 // summed device time per kernel class: out_ms[0..5] = load, potrf, trinv, trsm, update GEMM (k_gemm_nt), substitution;
 // out_ms[6] = number of k_gemm_nt update launches, out_ms[7] = algorithmic flops of those GEMMs.
+// reps < 0: keep the two-stream overlap (events on the main stream only: side-stream classes read ~0 and every wait for
+// the side stream is charged to the next main-stream launch) -- shows where the chain is delayed by the overlapped work.
 RCVD_API int32_t rcvd_debug_profile_linear(rcvd_problem* p, int32_t reps, double out_ms[8]) {
-  if (!p || !out_ms || reps <= 0) return set_err(RCVD_ERR_INVALID, "bad argument");
+  const bool keep_overlap = reps < 0; if (reps < 0) reps = -reps;
+  if (!p || !out_ms || reps == 0) return set_err(RCVD_ERR_INVALID, "bad argument");
   CK(cudaSetDevice(p->device));
   int rc = ensure_ready(p); if (rc) return rc;
-  const bool ov = p->overlap; p->overlap = false;
+  const bool ov = p->overlap; if (!keep_overlap) p->overlap = false;
   for (int i = 0; i < 8; ++i) out_ms[i] = 0.0;
   std::vector<std::pair<int, cudaEvent_t>> evs;
   for (int r = -1; r < reps; ++r) {
@@ -1105,7 +1116,7 @@ RCVD_API int32_t rcvd_debug_profile_linear(rcvd_problem* p, int32_t reps, double
     evs.clear(); p->prof = &evs;
     rc = enqueue_factor_solve(p);
     p->prof = nullptr;
-    cudaStreamSynchronize(p->stream);
+    cudaStreamSynchronize(p->stream); cudaStreamSynchronize(p->side_stream);
     double ngemm = 0;
     for (size_t i = 1; i < evs.size(); ++i) {
       float ms = 0; cudaEventElapsedTime(&ms, evs[i - 1].second, evs[i].second);
@@ -1165,6 +1176,8 @@ RCVD_API int32_t rcvd_debug_set_order_slack(rcvd_problem* p, int32_t slack) { if
 RCVD_API int32_t rcvd_debug_set_overlap(rcvd_problem* p, int32_t on) { if (!p) return RCVD_ERR_INVALID; p->overlap = on != 0; if (p->solve_graph) { cudaGraphExecDestroy(p->solve_graph); p->solve_graph = nullptr; } return RCVD_OK; }
 // Test / bench hook: 0 = explicit inverse + GEMM for the off-diagonal solves, 1 (default) = left-looking tensor-core TRSM.
 RCVD_API int32_t rcvd_debug_set_trsm_ll(rcvd_problem* p, int32_t on) { if (!p) return RCVD_ERR_INVALID; p->allow_trsm_ll = on != 0; p->structure_ready = false; return RCVD_OK; }
+// Test / bench hook: grid-size cap (CTAs) of one overlapped update launch on the side stream; 0 = unsliced.
+RCVD_API int32_t rcvd_debug_set_side_slice(rcvd_problem* p, int32_t ctas) { if (!p) return RCVD_ERR_INVALID; p->side_slice = ctas; if (p->solve_graph) { cudaGraphExecDestroy(p->solve_graph); p->solve_graph = nullptr; } return RCVD_OK; }
 RCVD_API int32_t rcvd_debug_set_fast_path(rcvd_problem* p, int32_t on) { if (!p) return RCVD_ERR_INVALID; p->use_fast = on != 0; return RCVD_OK; }
 RCVD_API int32_t rcvd_solve(rcvd_problem* p, const rcvd_solve_options* opt, rcvd_solve_summary* summary) {
   if (!p || !summary) return set_err(RCVD_ERR_INVALID, "null argument");

@@ -185,6 +185,13 @@ __device__ __forceinline__ void warp_chol16(double* __restrict__ D, double* __re
   }
 }
 
+#ifdef RCVD_POTRF_PHASES   // tools/potrf_phases.cu: cycle counts per phase of CTA 0 (thread 0's view)
+__device__ long long g_potrf_phase[8];
+#define POTRF_PHASE(n) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long now_ = clock64(); g_potrf_phase[n] += now_ - last_; last_ = now_; } } while (0)
+#else
+#define POTRF_PHASE(n) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(kPotrfSmemThreads) k_potrf_smem(double* __restrict__ Lb, double* __restrict__ invT,
                                                                    const int* __restrict__ frames, int npad, int* __restrict__ fail) {
   extern __shared__ __align__(16) double tiles[];
@@ -195,6 +202,9 @@ __global__ void __launch_bounds__(kPotrfSmemThreads) k_potrf_smem(double* __rest
   double* pinv = tiles + (size_t)ntl * kTileSz;     // [npad] reciprocal pivots (fits the spare 2 KB tile for npad <= 256)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = kPotrfSmemThreads / 32;
   const int g = lane >> 2, t = lane & 3;
+#ifdef RCVD_POTRF_PHASES
+  long long last_ = clock64();
+#endif
   // asynchronous tile load: 16-byte chunks (the swizzle keeps aligned pairs together), all in flight at once
   for (int idx = tid; idx < ntl * 128; idx += kPotrfSmemThreads) {
     const int tl = idx >> 7, e = idx & 127, r = e >> 3, c = (e & 7) * 2;
@@ -207,8 +217,10 @@ __global__ void __launch_bounds__(kPotrfSmemThreads) k_potrf_smem(double* __rest
   asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
+  POTRF_PHASE(0);
   if (warp == 0) warp_chol16(tiles, pinv, lane, fail);
   __syncthreads();
+  POTRF_PHASE(1);
   for (int jb = 0; jb < nt; ++jb) {
     const double* D = tiles + (size_t)(jb * (jb + 1) / 2 + jb) * kTileSz;
     const double* pv = pinv + jb * 16;
@@ -243,7 +255,9 @@ __global__ void __launch_bounds__(kPotrfSmemThreads) k_potrf_smem(double* __rest
 #pragma unroll
       for (int r = 0; r < 16; ++r) iT[(size_t)jb * 256 + r * 16 + cidx] = xcol[r];
     }
+    POTRF_PHASE(2);
     __syncthreads();
+    POTRF_PHASE(3);
     // ---- trailing update (DMMA) with lookahead: warp 0 updates tile (jb+1, jb+1) first and factors it at once ----
     const int m = nt - jb - 1, ntr = m * (m + 1) / 2;
     for (int tl = warp; tl < ntr; tl += nw) {
@@ -265,9 +279,11 @@ __global__ void __launch_bounds__(kPotrfSmemThreads) k_potrf_smem(double* __rest
           double2* ptr = reinterpret_cast<double2*>(&Ct[swz(i * 8 + g, j * 8 + 2 * t)]);
           double2 v = *ptr; v.x -= acc[i][j][0]; v.y -= acc[i][j][1]; *ptr = v;
         }
-      if (tl == 0) { __syncwarp(); warp_chol16(Ct, pinv + (jb + 1) * 16, lane, fail); }   // lookahead: next diagonal tile
+      if (tl == 0) { __syncwarp(); POTRF_PHASE(4); warp_chol16(Ct, pinv + (jb + 1) * 16, lane, fail); POTRF_PHASE(5); }   // lookahead: next diagonal tile
     }
+    POTRF_PHASE(6);
     __syncthreads();
+    POTRF_PHASE(7);
   }
   for (int idx = tid; idx < ntl * 128; idx += kPotrfSmemThreads) {
     const int tl = idx >> 7, e = idx & 127, r = e >> 3, c = (e & 7) * 2;

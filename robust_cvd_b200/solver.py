@@ -169,6 +169,9 @@ class Problem:
         """Test hook: False forces the generic accumulate kernel."""
         _check(self.L.rcvd_debug_set_fast_path(self.h, C.c_int32(1 if on else 0)))
 
+    def set_side_slice(self, ctas):
+        _check(self.L.rcvd_debug_set_side_slice(self.h, C.c_int32(ctas)))
+
     def set_trsm_ll(self, on=True):
         _check(self.L.rcvd_debug_set_trsm_ll(self.h, C.c_int32(1 if on else 0)))
 
