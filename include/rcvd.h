@@ -216,6 +216,33 @@ int32_t rcvd_depth_param_map(const rcvd_config* cfg, int32_t device, const doubl
 int32_t rcvd_spatial_warp(const rcvd_config* cfg, int32_t device, const double* spatial_params,
                           float* out, int32_t h, int32_t w);
 
+/* ---- flow-guided temporal depth filter ----
+ * Replaces DepthVideoProcessor::flowGuidedFilter (lib/Processor.cpp:315-590) for a consecutive frame range in one call.
+ * Arrays are indexed by a local frame index 0..num_frames-1 where index 0 is the absolute frame
+ * max(0, rangeFirst - frame_radius) (the reference reaches back that far, :395) and the range's last frame is
+ * first_out + num_out - 1 (no frame after it is read, :396-397).
+ *   depth     [num_frames][depth_height][depth_width] f32  transformed depth of the source stream (DepthFrame::depth())
+ *   cams      [num_frames][9] f32  extrinsics position xyz, orientation quaternion x,y,z,w, hFov, vFov (radians)
+ *   fwd_flow  [num_frames][height][width][2] f32, fwd_mask [num_frames][height][width] u8: slot i = flow/mask i -> i+1
+ *   bwd_flow / bwd_mask: slot i = flow/mask i -> i-1        (slots never reached by a chain may hold anything)
+ *   far_pairs [num_far][2] i32 local (source, target) indices, far_flow [num_far][height][width][2], far_mask [num_far][height][width]
+ *             (Params::farConnections, :415-427; may be NULL when num_far = 0)
+ *   out       [num_out][height][width] f32  filtered depth of frames first_out .. first_out + num_out - 1
+ * Float32 arithmetic in the reference's operation order; parity tolerance 1e-5 relative (libm expf/tanf, FMA contraction
+ * of the reference build are not pinned). */
+typedef struct rcvd_filter_params {
+  int32_t num_frames, first_out, num_out;
+  int32_t width, height, depth_width, depth_height;
+  int32_t frame_radius;   /* Params::frameRadius (lib/Processor.h:68) */
+  int32_t spatial_radius; /* Params::spatialRadius */
+  int32_t median;         /* Params::median: 0 weighted mean, 1 weighted median */
+  int32_t num_far;
+  float inv_aspect;       /* DepthVideo::invAspect() */
+} rcvd_filter_params;
+int32_t rcvd_flow_guided_filter(const rcvd_filter_params* prm, int32_t device, const float* depth, const float* cams,
+                                const float* fwd_flow, const uint8_t* fwd_mask, const float* bwd_flow, const uint8_t* bwd_mask,
+                                const int32_t* far_pairs, const float* far_flow, const uint8_t* far_mask, float* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,12 @@ def default_solve_options(max_iterations=1000, verbose=0):
         jacobi_scaling=1)
 
 
+class FilterParams(C.Structure):
+    """rcvd_filter_params (include/rcvd.h)."""
+    _fields_ = [(n, C.c_int32) for n in ("num_frames", "first_out", "num_out", "width", "height", "depth_width", "depth_height",
+                                         "frame_radius", "spatial_radius", "median", "num_far")] + [("inv_aspect", C.c_float)]
+
+
 def default_config(num_frames, aspect, **kw):
     """Config with the reference's Params defaults (lib/PoseOptimizer.h:55-103)."""
     focal_long = kw.pop("focal_long", 0.3461538376301239)

@@ -20,6 +20,8 @@
 #include "rcvd_eval.cuh"
 #include "rcvd_linalg.cuh"
 #include "rcvd_dense.cuh"
+#include "rcvd_filter.cuh"
+static int64_t g_filter_launches = 0;
 
 using namespace rcvd;
 
@@ -1229,3 +1231,86 @@ RCVD_API int32_t rcvd_spatial_warp(const rcvd_config* cfg, int32_t device, const
   Layout L; if (!cfg || !make_layout(*cfg, L)) return set_err(RCVD_ERR_INVALID, "unsupported transform configuration");
   return dense_run<2>(cfg, device, sp, L.ns, L.offS, nullptr, out, (size_t)w * h * 8, h, w);
 }
+
+// ---------------------------------------------------------------------------
+// Flow-guided temporal depth filter (rcvd_filter.cuh)
+// ---------------------------------------------------------------------------
+RCVD_API int32_t rcvd_flow_guided_filter(const rcvd_filter_params* prm, int32_t device, const float* depth, const float* cams,
+                                         const float* fwd_flow, const uint8_t* fwd_mask, const float* bwd_flow, const uint8_t* bwd_mask,
+                                         const int32_t* far_pairs, const float* far_flow, const uint8_t* far_mask, float* out) {
+  if (!prm || !depth || !cams || !out) return set_err(RCVD_ERR_INVALID, "null argument");
+  const rcvd_filter_params& q = *prm;
+  if (q.num_frames <= 0 || q.num_out <= 0 || q.first_out < 0 || q.first_out + q.num_out > q.num_frames || q.width <= 0 || q.height <= 0 ||
+      q.depth_width <= 0 || q.depth_height <= 0 || q.frame_radius < 0 || q.spatial_radius < 0 || q.num_far < 0 || !(q.inv_aspect > 0.f))
+    return set_err(RCVD_ERR_INVALID, "bad filter parameters");
+  if (q.frame_radius > 0 && q.num_frames > 1 && (!fwd_flow || !fwd_mask || !bwd_flow || !bwd_mask)) return set_err(RCVD_ERR_INVALID, "flow stacks missing");
+  if (q.num_far > 0 && (!far_pairs || !far_flow || !far_mask)) return set_err(RCVD_ERR_INVALID, "far-connection arrays missing");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev)
+    return set_err(RCVD_ERR_NO_DEVICE, "no usable CUDA device (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device ordinal out of range");
+  CK(cudaSetDevice(device));
+  const int F = q.num_frames; const size_t plane = (size_t)q.width * q.height, dplane = (size_t)q.depth_width * q.depth_height;
+  // cameras: tan(fov / 2) in float on the host, like DepthVideo::project (lib/DepthVideo.cpp:640-641)
+  std::vector<float> hc((size_t)F * 12, 0.f);
+  for (int f = 0; f < F; ++f) {
+    for (int i = 0; i < 7; ++i) hc[(size_t)f * 12 + i] = cams[(size_t)f * 9 + i];
+    hc[(size_t)f * 12 + 7] = std::tan(cams[(size_t)f * 9 + 7] / 2.f);
+    hc[(size_t)f * 12 + 8] = std::tan(cams[(size_t)f * 9 + 8] / 2.f);
+  }
+  // far connections grouped by source frame (stable: the caller's order within a frame is kept)
+  std::vector<int> far_begin(F + 1, 0), order(q.num_far), pairs_sorted((size_t)2 * q.num_far);
+  int maxfar = 0;
+  for (int k = 0; k < q.num_far; ++k) {
+    const int s = far_pairs[2 * k], d = far_pairs[2 * k + 1];
+    if (s < 0 || s >= F || d < 0 || d >= F) return set_err(RCVD_ERR_INVALID, "far connection %d out of range", k);
+    far_begin[s + 1]++;
+  }
+  for (int f = 0; f < F; ++f) { maxfar = std::max(maxfar, far_begin[f + 1]); far_begin[f + 1] += far_begin[f]; }
+  { std::vector<int> cur(far_begin.begin(), far_begin.end() - 1); for (int k = 0; k < q.num_far; ++k) order[cur[far_pairs[2 * k]]++] = k; }
+  cudaStream_t st; CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  std::vector<void*> bufs;
+  auto dev = [&](size_t bytes) -> void* { void* ptr = nullptr; if (cudaMallocAsync(&ptr, std::max<size_t>(bytes, 16), st) != cudaSuccess) return nullptr; bufs.push_back(ptr); return ptr; };
+  auto up = [&](const void* src, size_t bytes) -> void* { void* d = dev(bytes); if (d && src && bytes) cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st); return d; };
+  FilterArgs a{};
+  a.depth = (const float*)up(depth, (size_t)F * dplane * 4);
+  a.cams = (const float*)up(hc.data(), hc.size() * 4);
+  const bool chains = q.frame_radius > 0 && F > 1;
+  a.fwd_flow = (const float*)up(chains ? fwd_flow : nullptr, chains ? (size_t)F * plane * 8 : 0); a.fwd_mask = (const uint8_t*)up(chains ? fwd_mask : nullptr, chains ? (size_t)F * plane : 0);
+  a.bwd_flow = (const float*)up(chains ? bwd_flow : nullptr, chains ? (size_t)F * plane * 8 : 0); a.bwd_mask = (const uint8_t*)up(chains ? bwd_mask : nullptr, chains ? (size_t)F * plane : 0);
+  if (q.num_far > 0) {
+    float* ff = (float*)dev((size_t)q.num_far * plane * 8); uint8_t* fm = (uint8_t*)dev((size_t)q.num_far * plane);
+    if (ff && fm)
+      for (int k = 0; k < q.num_far; ++k) {   // sorted order on the device
+        cudaMemcpyAsync(ff + (size_t)k * plane * 2, far_flow + (size_t)order[k] * plane * 2, plane * 8, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(fm + (size_t)k * plane, far_mask + (size_t)order[k] * plane, plane, cudaMemcpyHostToDevice, st);
+        pairs_sorted[2 * k] = far_pairs[2 * order[k]]; pairs_sorted[2 * k + 1] = far_pairs[2 * order[k] + 1];
+      }
+    a.far_flow = ff; a.far_mask = fm;
+    a.far_pairs = (const int*)up(pairs_sorted.data(), pairs_sorted.size() * 4);
+    a.far_begin = (const int*)up(far_begin.data(), far_begin.size() * 4);
+  }
+  a.out = (float*)dev((size_t)q.num_out * plane * 4);
+  const int win = 2 * q.spatial_radius + 1;
+  a.max_samples = win * win * (1 + 2 * q.frame_radius + maxfar);
+  if (q.median) a.scratch = (float2*)dev((size_t)q.num_out * plane * a.max_samples * sizeof(float2));
+  bool ok = true; for (void* b : bufs) ok = ok && b != nullptr;
+  int rc = RCVD_OK;
+  if (!ok) rc = set_err(RCVD_ERR_CUDA, "device allocation failed in rcvd_flow_guided_filter");
+  else {
+    cudaMemsetAsync(a.out, 0, (size_t)q.num_out * plane * 4, st);
+    a.F = F; a.first_out = q.first_out; a.num_out = q.num_out; a.last_frame = q.first_out + q.num_out - 1;
+    a.w = q.width; a.h = q.height; a.wd = q.depth_width; a.hd = q.depth_height;
+    a.frame_radius = q.frame_radius; a.spatial_radius = q.spatial_radius; a.median = q.median; a.inv_aspect = q.inv_aspect;
+    const dim3 grid((q.width + 31) / 32, (q.height + 3) / 4, q.num_out);
+    if (q.median) k_flow_guided_filter<true><<<grid, 128, 0, st>>>(a); else k_flow_guided_filter<false><<<grid, 128, 0, st>>>(a);
+    g_filter_launches++;
+    e = cudaMemcpyAsync(out, a.out, (size_t)q.num_out * plane * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = set_err(RCVD_ERR_CUDA, "flow-guided filter failed: %s", cudaGetErrorString(e));
+  }
+  for (void* b : bufs) cudaFreeAsync(b, st);
+  cudaStreamSynchronize(st); cudaStreamDestroy(st);
+  return rc;
+}
+RCVD_API int64_t rcvd_filter_launch_count() { return g_filter_launches; }

@@ -214,6 +214,31 @@ def spatial_warp(cfg, spatial_params, h, w, device=0):
     return out
 
 
+def flow_guided_filter(depth, cams, fwd_flow, fwd_mask, bwd_flow, bwd_mask, first_out, num_out, frame_radius, spatial_radius=0, median=False,
+                       inv_aspect=1.0, far_pairs=None, far_flow=None, far_mask=None, device=0):
+    """rcvd_flow_guided_filter (DepthVideoProcessor::flowGuidedFilter, reference lib/Processor.cpp:315-590) on the GPU.
+    depth [F,hd,wd] f32, cams [F,9] f32, flows [F,h,w,2] f32, masks [F,h,w] u8 -> filtered depth [num_out,h,w] f32."""
+    depth = np.ascontiguousarray(depth, np.float32); cams = np.ascontiguousarray(cams, np.float32)
+    F, hd, wd = depth.shape
+    arrs = []
+    for a, dt in ((fwd_flow, np.float32), (fwd_mask, np.uint8), (bwd_flow, np.float32), (bwd_mask, np.uint8), (far_flow, np.float32), (far_mask, np.uint8)):
+        arrs.append(None if a is None else np.ascontiguousarray(a, dt))
+    ff, fm, bf, bm, rf, rm = arrs
+    ref_mask = fm if fm is not None else rm
+    if ref_mask is None:
+        raise ValueError("flow masks are needed to define the output resolution")
+    h, w = ref_mask.shape[1:3]
+    nfar = 0 if far_pairs is None else len(far_pairs)
+    fp = None if nfar == 0 else np.ascontiguousarray(far_pairs, np.int32).reshape(-1, 2)
+    prm = abi.FilterParams(num_frames=F, first_out=first_out, num_out=num_out, width=w, height=h, depth_width=wd, depth_height=hd,
+                           frame_radius=frame_radius, spatial_radius=spatial_radius, median=1 if median else 0, num_far=nfar, inv_aspect=inv_aspect)
+    out = np.zeros((num_out, h, w), np.float32)
+    _check(lib().rcvd_flow_guided_filter(C.byref(prm), C.c_int32(device), _p(depth, C.c_float), _p(cams, C.c_float),
+                                         _p(ff, C.c_float), _p(fm, C.c_uint8), _p(bf, C.c_float), _p(bm, C.c_uint8),
+                                         _p(fp, C.c_int32), _p(rf, C.c_float), _p(rm, C.c_uint8), _p(out, C.c_float)))
+    return out
+
+
 def fp64_tensor_peak(device=0):
     """Bench hook: live-measured fp64 tensor-core (DMMA) peak of `device` in TFLOP/s."""
     v = C.c_double()
