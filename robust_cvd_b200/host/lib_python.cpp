@@ -7,6 +7,7 @@
 #include <pybind11/stl.h>
 
 #include "model.h"
+#include <cstring>
 
 namespace py = pybind11;
 using namespace rcvdh;
@@ -85,6 +86,13 @@ PYBIND11_MODULE(lib_python, m) {
   py::class_<DepthFrame>(m, "DepthFrame")
       .def("depth", [](DepthFrame& f) { return imageToNp(f.depth()); })
       .def("sourceDepth", [](DepthFrame& f) { return imageToNp(f.sourceDepth()); })
+      .def("setDepth", [](DepthFrame& f, py::array_t<float, py::array::c_style | py::array::forcecast> a) {
+        if (a.ndim() != 2) throw std::runtime_error("Depth image must be a 2-D float32 array.");
+        Image img; img.create(int(a.shape(0)), int(a.shape(1)), cvMakeType(CV_32F, 1));
+        std::memcpy(img.ptr<float>(), a.data(), size_t(a.shape(0)) * a.shape(1) * sizeof(float));
+        f.setDepth(img);
+      })
+      .def("clear", &DepthFrame::clear)
       .def("clearCache", &DepthFrame::clearCache).def("clearXformedCache", &DepthFrame::clearXformedCache)
       .def("depthXform", [](DepthFrame& f) -> Xform& { return f.depthXform(); }, py::return_value_policy::reference)
       .def("resetDepthXform", &DepthFrame::resetDepthXform)
@@ -100,7 +108,7 @@ PYBIND11_MODULE(lib_python, m) {
 
   py::class_<DepthVideo>(m, "DepthVideo")
       .def(py::init<>())
-      .def("printInfo", &DepthVideo::printInfo).def("save", &DepthVideo::save)
+      .def("printInfo", &DepthVideo::printInfo).def("save", &DepthVideo::save).def("load", &DepthVideo::load).def("saveDepth", &DepthVideo::saveDepth)
       .def("width", &DepthVideo::width).def("height", &DepthVideo::height).def("aspect", &DepthVideo::aspect).def("invAspect", &DepthVideo::invAspect)
       .def("path", &DepthVideo::path).def("numFrames", &DepthVideo::numFrames)
       .def("numColorStreams", &DepthVideo::numColorStreams).def("hasColorStream", &DepthVideo::hasColorStream).def("colorStreamIndex", &DepthVideo::colorStreamIndex)
@@ -212,6 +220,7 @@ PYBIND11_MODULE(lib_python, m) {
       .value("ResetNormalizeOptimize", Op::ResetNormalizeOptimize);
   dvp.def(py::init<DepthVideo*>(), py::keep_alive<1, 2>())
       .def("process", &DepthVideoProcessor::process).def("gridXformSplit", &DepthVideoProcessor::gridXformSplit)
+      .def("reset", &DepthVideoProcessor::reset).def("copy", &DepthVideoProcessor::copy).def("flowGuidedFilter", &DepthVideoProcessor::flowGuidedFilter)
       .def("resetPoses", &DepthVideoProcessor::resetPoses).def("resetDepthXforms", &DepthVideoProcessor::resetDepthXforms)
       .def("resetSpatialXforms", &DepthVideoProcessor::resetSpatialXforms)
       .def("normalizeDepth", &DepthVideoProcessor::normalizeDepth).def("optimizePoses", &DepthVideoProcessor::optimizePoses);
@@ -224,6 +233,7 @@ PYBIND11_MODULE(lib_python, m) {
     Image im; im.create((int)b.shape(0), (int)b.shape(1), cvMakeType(CV_8U, 1)); std::memcpy(im.data.data(), b.data(), im.data.size());
     Image r = distanceTransformL2_5(im); return imageToNp(&r); });
   m.def("_imreadPng", [](const std::string& f, bool gray) { Image im = imreadPng(f, gray); return imageToNp(im.empty() ? nullptr : &im); });
+  m.def("_makeQuat", [](float x, float y, float z, float w) { Quatf q; q.x = x; q.y = y; q.z = z; q.w = w; return q; });   // tests: the reference binds no quaternion constructor
   m.def("_quatToAngleAxis", [](float x, float y, float z, float w) { Quatf q; q.x = x; q.y = y; q.z = z; q.w = w; double aa[3]; quatToAngleAxis(q, aa); return py::make_tuple(aa[0], aa[1], aa[2]); });
   m.def("_angleAxisToQuat", [](double a, double b, double c) { const double aa[3] = {a, b, c}; Quatf q = angleAxisToQuat(aa); return py::make_tuple(q.x, q.y, q.z, q.w); });
 }

@@ -19,6 +19,10 @@ static bool g_logStdout = false;
 void setLogToStdout(bool v) { g_logStdout = v; }
 void logInfo(const std::string& s) { (g_logStdout ? std::cout : std::cerr) << s << std::endl; }
 static bool fileExists(const std::string& f) { struct stat st; return stat(f.c_str(), &st) == 0; }
+static void makeDirs(const std::string& dir) {   // mkdir -p
+  for (size_t pos = 1; pos <= dir.size(); ++pos)
+    if (pos == dir.size() || dir[pos] == '/') { const std::string sub = dir.substr(0, pos); if (!fileExists(sub)) ::mkdir(sub.c_str(), 0777); }
+}
 static std::string fmtInt6(int v) { char b[32]; snprintf(b, sizeof(b), "%06d", v); return b; }
 
 // Eigen::Quaternion::_transformVector: v + 2w (q x v) + 2 q x (q x v), float arithmetic
@@ -342,6 +346,13 @@ const Image* DepthFrame::depth() {
   if (!xformed_) { const Image* s = sourceDepth(); if (!s) return nullptr; xformed_ = std::make_unique<Image>(depthXform_->apply(*s)); }
   return xformed_.get();
 }
+void DepthFrame::setDepth(const Image& depth) {
+  if (depth.type != cvMakeType(CV_32F, 1)) throw std::runtime_error("Depth image has incorrect type.");
+  if (stream_.width_ < 0) { stream_.width_ = depth.cols; stream_.height_ = depth.rows; }
+  else if (stream_.width_ != depth.cols || stream_.height_ != depth.rows) throw std::runtime_error("Depth frame has inconsistent dimensions.");
+  source_ = std::make_unique<Image>(depth); sourceLoaded_ = true; xformed_.reset();
+}
+void DepthFrame::clear() { clearCache(); intrinsics = Intrinsics(); extrinsics = Extrinsics(); }
 DepthFrame& DepthStream::frame(int i) { if (i < 0 || i >= int(frames_.size())) throw std::runtime_error("Frame index out of range."); return *frames_[i]; }
 void DepthStream::setDir(const std::string& dir) { dir_ = dir; path_ = video_.path() + "/" + dir_; }
 int DepthStream::width() { if (width_ < 0) { for (auto& f : frames_) if (f->sourceDepth()) break; if (width_ < 0) width_ = height_ = 0; } return width_; }
@@ -410,6 +421,74 @@ void DepthVideo::save() {
   }
   wr<float>(os, duration_); wr<int32_t>(os, width_); wr<int32_t>(os, height_); wr<float>(os, aspect_); wr<float>(os, invAspect_);
   wr<uint32_t>(os, 0xDEADBEEF);
+}
+// Reader for the file save() writes.  Note: the reference's own load() (lib/DepthVideo.cpp:120-298) does not consume the
+// per-stream "has GOP table" byte that its save() emits (:329-332, :355-359 vs the commented-out reads at :191-197, :236-245),
+// so it cannot re-read format-13 files; this reader follows the WRITER's layout.
+template <class T> static T rd(std::istream& is) { T v{}; is.read(reinterpret_cast<char*>(&v), sizeof(T)); if (!is) throw std::runtime_error("Unexpected end of 'video.dat'."); return v; }
+static std::string rdstr(std::istream& is) { const uint64_t n = rd<uint64_t>(is); if (n > (1u << 20)) throw std::runtime_error("Corrupt string in 'video.dat'."); std::string s(n, '\0'); is.read(s.data(), n); if (!is) throw std::runtime_error("Unexpected end of 'video.dat'."); return s; }
+static XformDescriptor rdXformDesc(std::istream& is) { XformDescriptor d; d.type = XformType(rd<int32_t>(is)); const std::string str = rdstr(is); const XformType t = d.type; d.parse(str); d.type = t; return d; }
+void DepthVideo::load(const std::string& path) {
+  std::ifstream is(path + "/video.dat", std::ios::binary);
+  if (!is) throw std::runtime_error("Could not find 'video.dat'.");
+  if (rd<uint32_t>(is) != 0xDEADBEEF) throw std::runtime_error("Did not see magic marker at beginning of file.");
+  const uint32_t fileFormat = rd<uint32_t>(is), dpFormat = rd<uint32_t>(is);
+  if (fileFormat > 13) throw std::runtime_error("File format too new.");
+  if (fileFormat < 13 || dpFormat != 3) throw std::runtime_error("File format too old.");   // only the current writer's format is supported here
+  colorStreams_.clear(); depthStreams_.clear(); path_ = path;
+  const int n = rd<int32_t>(is); if (n < 0 || n > (1 << 24)) throw std::runtime_error("Corrupt frame count in 'video.dat'.");
+  pts_.resize(n); for (float& p : pts_) p = rd<float>(is);
+  const int ncs = rd<int32_t>(is);
+  for (int i = 0; i < ncs; ++i) {
+    colorStreams_.push_back(std::make_unique<ColorStream>(*this));
+    ColorStream& cs = *colorStreams_.back();
+    cs.name_ = rdstr(is); cs.setDir(rdstr(is)); cs.extension_ = rdstr(is); cs.type_ = rd<int32_t>(is); cs.width_ = rd<int32_t>(is); cs.height_ = rd<int32_t>(is);
+    if (rd<bool>(is)) throw std::runtime_error("GOP tables are not supported.");
+    for (int f = 0; f < n; ++f) cs.frames_.push_back(std::make_unique<ColorFrame>(cs, f));
+  }
+  const int nds = rd<int32_t>(is);
+  for (int i = 0; i < nds; ++i) {
+    depthStreams_.push_back(std::make_unique<DepthStream>(*this));
+    DepthStream& ds = *depthStreams_.back();
+    ds.name_ = rdstr(is); ds.setDir(rdstr(is)); ds.depthXformDesc_ = rdXformDesc(is); ds.spatialXformDesc_ = rdXformDesc(is);
+    ds.width_ = rd<int32_t>(is); ds.height_ = rd<int32_t>(is);
+    if (rd<bool>(is)) throw std::runtime_error("GOP tables are not supported.");
+    for (int f = 0; f < n; ++f) {
+      ds.frames_.push_back(std::make_unique<DepthFrame>(*this, ds, f));
+      DepthFrame& df = *ds.frames_.back();
+      if (rd<int32_t>(is) != 0) throw std::runtime_error("Only perspective intrinsics are supported.");
+      df.intrinsics.vFov = rd<float>(is); df.intrinsics.hFov = rd<float>(is); df.intrinsics.centerLat = rd<float>(is); df.intrinsics.centerLon = rd<float>(is);
+      df.extrinsics.position.x = rd<float>(is); df.extrinsics.position.y = rd<float>(is); df.extrinsics.position.z = rd<float>(is);
+      df.extrinsics.orientation.x = rd<float>(is); df.extrinsics.orientation.y = rd<float>(is); df.extrinsics.orientation.z = rd<float>(is); df.extrinsics.orientation.w = rd<float>(is);
+      df.enabled = rd<bool>(is);
+      for (int k = 0; k < 2; ++k) {
+        const XformDescriptor d = rdXformDesc(is);
+        if (k == 0 && d != ds.depthXformDesc_) throw std::runtime_error("Inconsistent depth transform.");
+        Xform& x = k == 0 ? df.depthXform() : df.spatialXform();
+        if (d != x.desc()) throw std::runtime_error("Inconsistent spatial transform.");
+        is.read(reinterpret_cast<char*>(x.params().data()), sizeof(double) * x.params().size());
+        if (!is) throw std::runtime_error("Unexpected end of 'video.dat'.");
+      }
+    }
+  }
+  duration_ = rd<float>(is); width_ = rd<int32_t>(is); height_ = rd<int32_t>(is); aspect_ = rd<float>(is); invAspect_ = rd<float>(is);
+  if (rd<uint32_t>(is) != 0xDEADBEEF) throw std::runtime_error("Did not see magic marker at end of file.");
+}
+void DepthVideo::saveDepth(int stream) {
+  DepthStream& ds = depthStream(stream);
+  for (int f = 0; f < numFrames(); ++f) {
+    const std::string fn = ds.path() + "/depth/frame_" + fmtInt6(f) + ".raw";
+    const Image* d = ds.frame(f).depth();
+    if (d) {
+      Image disp; disp.create(d->rows, d->cols, cvMakeType(CV_32F, 1));
+      const float* s = d->ptr<float>(); float* o = disp.ptr<float>();
+      for (size_t i = 0; i < size_t(d->rows) * d->cols; ++i) o[i] = (std::isfinite(s[i]) && s[i] > 0.f) ? 1.f / s[i] : 0.f;   // invalid depth -> 0 (:611-618)
+      makeDirs(ds.path() + "/depth");
+      fwriteim(fn, disp);
+    } else if (fileExists(fn)) {
+      std::remove(fn.c_str());
+    }
+  }
 }
 void importVideo(DepthVideo& video, const std::string& path, bool discoverStreams) {
   logInfo("Importing 3D video '" + path + "'...");

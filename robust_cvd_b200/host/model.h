@@ -163,6 +163,8 @@ class DepthFrame {
   DepthFrame(const DepthFrame&) = delete;
   const Image* sourceDepth();          // depth = 1/disparity from depth/frame_%06d.raw (lib/DepthStream.cpp:193-216)
   const Image* depth();                // transformed depth (lib/DepthStream.cpp:266-290)
+  void setDepth(const Image& depth);   // becomes the new source depth; transformed caches dropped (lib/DepthStream.cpp:102-116)
+  void clear();                        // caches + default intrinsics / extrinsics (:145-149)
   void clearCache() { source_.reset(); sourceLoaded_ = false; xformed_.reset(); }
   void clearXformedCache() { xformed_.reset(); }
   Xform& depthXform() { return *depthXform_; }
@@ -209,6 +211,8 @@ class DepthVideo {
   DepthVideo(const DepthVideo&) = delete;
   void init(const std::string& path, int width, int height, const std::vector<float>& pts);   // lib/DepthVideo.cpp:103-119
   void save();                                                                                 // :300-385 (video.dat)
+  void load(const std::string& path);                                                          // :120-298 (video.dat as written by save())
+  void saveDepth(int stream);                                                                  // :597-635 (depth/frame_%06d.raw as disparity)
   void printInfo() const;
   int width() const { return width_; }
   int height() const { return height_; }
@@ -320,13 +324,17 @@ class DepthVideoProcessor {
                   ResetSpatialXforms, NormalizeDepth, OptimizePoses, ResetNormalizeOptimize };
   struct Params {   // lib/Processor.h:60-90
     Op op = Op::None; FrameRange frameRange; int colorStream = 0, depthStream = 0, sourceDepthStream = 0;
-    int spatialRadius = 2, frameRadius = 2; float depthSigma = 0.02f, colorSigma = 0.05f; bool median = false; bool farConnections = false;
-    int matchSeparation = 10; float flowConsistancyThresh = 1.f; int trackSpawnDistance = 10, trackPruneDistance = 5;
-    float minDynamicDistance = -1.f; int minTrackLength = 3;
+    int spatialRadius = 0, frameRadius = 2; float depthSigma = 0.3f, colorSigma = 0.0f; bool median = false; bool farConnections = false;
+    float maxDepth = 1000.f;
+    int matchSeparation = 10; float flowConsistancyThresh = 0.05f; int trackSpawnDistance = 20, trackPruneDistance = 5;
+    int minDynamicDistance = 3; int minTrackLength = 4;
     XformDescriptor depthXformDesc, spatialXformDesc; DepthVideoPoseOptimizer::Params poseOptimizer;
   };
   explicit DepthVideoProcessor(DepthVideo* video) : video_(video) {}
   void process(const Params& params);
+  void reset(const Params& params);               // lib/Processor.cpp:146-150
+  void copy(const Params& params);                // :152-180
+  void flowGuidedFilter(const Params& params);    // :315-590, on the GPU (rcvd_flow_guided_filter)
   void gridXformSplit(const Params& params);      // lib/Processor.cpp:888-985
   void resetPoses(const Params& params);          // :987-1003
   void resetDepthXforms(const Params& params);    // :1005-1008

@@ -4,6 +4,8 @@
 // problem assembly from the DepthVideo + FlowConstraintsCollection, coarse-to-fine schedule, pose
 // write-back -- but "ceres::Solve" is the CUDA library behind include/rcvd.h.  No CPU solver here.
 #include "model.h"
+#include <dirent.h>
+#include <cstring>
 
 #include <algorithm>
 #include <cmath>
@@ -285,9 +287,125 @@ void DepthVideoProcessor::process(const Params& params) {   // lib/Processor.cpp
     case Op::ResetPoses: resetPoses(params); break;
     case Op::ResetDepthXforms: resetDepthXforms(params); break;
     case Op::ResetSpatialXforms: resetSpatialXforms(params); break;
-    case Op::Reset: case Op::Copy: case Op::BilateralFilter: case Op::FlowGuidedFilter:
-      throw std::runtime_error("This operation (depth filters / copy) is outside the pose-optimization path and is not implemented in this build.");
+    case Op::Reset: reset(params); break;
+    case Op::Copy: copy(params); break;
+    case Op::FlowGuidedFilter: flowGuidedFilter(params); break;
+    case Op::BilateralFilter:
+      throw std::runtime_error("The bilateral depth filter is outside the pose-optimization path and is not implemented in this build.");
     default: throw std::runtime_error("Unsupported operation selected.");
+  }
+}
+void DepthVideoProcessor::reset(const Params& params) {   // :146-150
+  for (int frame : params.frameRange.frames) video_->depthFrame(params.depthStream, frame).clear();
+}
+void DepthVideoProcessor::copy(const Params& params) {   // :152-180
+  if (params.sourceDepthStream < 0 || params.sourceDepthStream >= video_->numDepthStreams()) throw std::runtime_error("Source depth stream out of range.");
+  if (params.sourceDepthStream == params.depthStream) throw std::runtime_error("Source and destination depth stream cannot be identical.");
+  DepthStream& srcDs = video_->depthStream(params.sourceDepthStream);
+  DepthStream& dstDs = video_->depthStream(params.depthStream);
+  for (int frame : params.frameRange.frames) {
+    DepthFrame& src = srcDs.frame(frame); DepthFrame& dst = dstDs.frame(frame);
+    const Image* depth = src.depth();
+    if (!depth) throw std::runtime_error("Source depth frame " + std::to_string(frame) + " has no depth image.");
+    dst.setDepth(*depth);
+    dst.intrinsics = src.intrinsics; dst.extrinsics = src.extrinsics;
+  }
+}
+// Flow-guided temporal filter (:315-590).  The reference walks frame by frame and pixel by pixel on the CPU; here the host
+// gathers the depth images, cameras and consecutive-frame flows of the whole range once and one kernel launch
+// (rcvd_flow_guided_filter, csrc/rcvd_filter.cuh) filters every frame.
+void DepthVideoProcessor::flowGuidedFilter(const Params& params) {
+  logInfo("Applying flow guided filter...");
+  if (!params.frameRange.isConsecutive()) throw std::runtime_error("Frame range must be consecutive.");
+  params.frameRange.checkEmpty();
+  ColorStream& cs = video_->colorStream("down");
+  const int w = cs.width(), h = cs.height();
+  if (w <= 0 || h <= 0) throw std::runtime_error("Color stream 'down' has no frames.");
+  DepthStream& srcDs = video_->depthStream(params.sourceDepthStream);
+  DepthStream& dstDs = video_->depthStream(params.depthStream);
+  const int first = params.frameRange.firstFrame(), last = params.frameRange.lastFrame();
+  if (params.sourceDepthStream == params.depthStream)   // the reference would then read frames it has already filtered (order dependent)
+    throw std::runtime_error("Source and destination depth stream cannot be identical.");
+  // frames held on the device: the temporal windows of the range, or the whole video when far connections may point anywhere
+  const int winBase = std::max(0, first - params.frameRadius);
+  const int base = params.farConnections ? 0 : winBase, F = (params.farConnections ? video_->numFrames() - 1 : last) - base + 1;
+  const size_t plane = size_t(w) * h;
+  auto flowFile = [&](int a, int b) { char buf[64]; snprintf(buf, sizeof(buf), "/flow/flow_%06d_%06d.raw", a, b); return video_->path() + buf; };
+  auto maskFile = [&](int a, int b) { char buf[64]; snprintf(buf, sizeof(buf), "/flow_mask/mask_%06d_%06d.png", a, b); return video_->path() + buf; };
+  auto loadPair = [&](int a, int b, float* flowDst, uint8_t* maskDst, bool required) -> bool {
+    Image flow, mask;
+    bool ok = false;
+    try {
+      freadim(flowFile(a, b), flow); mask = imreadPng(maskFile(a, b), true);
+      ok = flow.cols == w && flow.rows == h && flow.type == cvMakeType(CV_32F, 2) && mask.cols == w && mask.rows == h;
+    } catch (const std::exception&) { ok = false; }
+    if (!ok) { if (required) throw std::runtime_error("Missing or mismatched flow / flow mask for frames " + std::to_string(a) + " -> " + std::to_string(b) + "."); return false; }
+    std::memcpy(flowDst, flow.ptr<float>(), plane * 2 * sizeof(float)); std::memcpy(maskDst, mask.ptr<uint8_t>(), plane);
+    return true;
+  };
+  // depth + cameras of frames base .. last
+  int wd = -1, hd = -1;
+  std::vector<float> depth, cams(size_t(F) * 9);
+  for (int i = 0; i < F; ++i) {
+    DepthFrame& df = srcDs.frame(base + i);
+    const Image* d = df.depth();
+    if (!d) throw std::runtime_error("Source depth frame " + std::to_string(base + i) + " has no depth image.");
+    if (wd < 0) { wd = d->cols; hd = d->rows; depth.resize(size_t(F) * wd * hd); }
+    if (d->cols != wd || d->rows != hd) throw std::runtime_error("Depth frame has inconsistent dimensions.");
+    std::memcpy(depth.data() + size_t(i) * wd * hd, d->ptr<float>(), size_t(wd) * hd * sizeof(float));
+    float* c = cams.data() + size_t(i) * 9;
+    c[0] = df.extrinsics.position.x; c[1] = df.extrinsics.position.y; c[2] = df.extrinsics.position.z;
+    c[3] = df.extrinsics.orientation.x; c[4] = df.extrinsics.orientation.y; c[5] = df.extrinsics.orientation.z; c[6] = df.extrinsics.orientation.w;
+    c[7] = df.intrinsics.hFov; c[8] = df.intrinsics.vFov;
+  }
+  // consecutive-frame flows: slot i holds (base+i -> base+i+1) resp. (base+i -> base+i-1); every slot a chain can reach is required (:405-413 CHECKs)
+  std::vector<float> fwd, bwd; std::vector<uint8_t> fwdMask, bwdMask;
+  if (params.frameRadius > 0 && F > 1) {
+    fwd.assign(size_t(F) * plane * 2, 0.f); bwd.assign(size_t(F) * plane * 2, 0.f); fwdMask.assign(size_t(F) * plane, 0); bwdMask.assign(size_t(F) * plane, 0);
+    for (int f = winBase; f < last; ++f) {
+      const int i = f - base;
+      if (f >= first) loadPair(f, f + 1, fwd.data() + size_t(i) * plane * 2, fwdMask.data() + size_t(i) * plane, true);    // forward chains start at frames >= first
+      loadPair(f + 1, f, bwd.data() + size_t(i + 1) * plane * 2, bwdMask.data() + size_t(i + 1) * plane, true);
+    }
+  }
+  // far connections (:415-427): every flow file (frame, fi) with fi outside the temporal window of `frame`
+  std::vector<int32_t> farPairs; std::vector<float> farFlow; std::vector<uint8_t> farMask;
+  if (params.farConnections) {
+    std::vector<std::pair<int, int>> flowPairs;
+    if (DIR* dir = opendir((video_->path() + "/flow").c_str())) {
+      while (dirent* e = readdir(dir)) {
+        const std::string name = e->d_name; const size_t dot = name.rfind('.');
+        const std::string stem = dot == std::string::npos ? name : name.substr(0, dot);
+        if (stem.size() != 18 || stem.substr(0, 5) != "flow_") continue;
+        flowPairs.emplace_back(std::stoi(stem.substr(5, 6)), std::stoi(stem.substr(12, 6)));
+      }
+      closedir(dir);
+    }
+    std::sort(flowPairs.begin(), flowPairs.end());   // directory order is unspecified in the reference; sorted here
+    for (const auto& pr : flowPairs) {
+      const int frame = pr.first, fi = pr.second;
+      if (frame < first || frame > last || fi < 0 || fi >= video_->numFrames()) continue;
+      const int f0 = std::max(0, frame - params.frameRadius), f1 = std::min(last, frame + params.frameRadius);
+      if (!(fi < f0 || fi > f1)) continue;
+      const size_t k = farPairs.size() / 2;
+      farFlow.resize((k + 1) * plane * 2); farMask.resize((k + 1) * plane);
+      if (!loadPair(frame, fi, farFlow.data() + k * plane * 2, farMask.data() + k * plane, false)) { farFlow.resize(k * plane * 2); farMask.resize(k * plane); continue; }
+      farPairs.push_back(frame - base); farPairs.push_back(fi - base);
+    }
+  }
+  rcvd_filter_params prm{};
+  prm.num_frames = F; prm.first_out = first - base; prm.num_out = last - first + 1; prm.width = w; prm.height = h; prm.depth_width = wd; prm.depth_height = hd;
+  prm.frame_radius = params.frameRadius; prm.spatial_radius = params.spatialRadius; prm.median = params.median ? 1 : 0; prm.num_far = int(farPairs.size() / 2);
+  prm.inv_aspect = video_->invAspect();
+  std::vector<float> out(size_t(prm.num_out) * plane);
+  const int rc = rcvd_flow_guided_filter(&prm, 0, depth.data(), cams.data(), fwd.empty() ? nullptr : fwd.data(), fwdMask.empty() ? nullptr : fwdMask.data(),
+                                         bwd.empty() ? nullptr : bwd.data(), bwdMask.empty() ? nullptr : bwdMask.data(),
+                                         farPairs.empty() ? nullptr : farPairs.data(), farFlow.empty() ? nullptr : farFlow.data(), farMask.empty() ? nullptr : farMask.data(), out.data());
+  if (rc != RCVD_OK) throw std::runtime_error(std::string("flow guided filter failed: ") + rcvd_last_error());
+  for (int i = 0; i < prm.num_out; ++i) {
+    Image img; img.create(h, w, cvMakeType(CV_32F, 1));
+    std::memcpy(img.ptr<float>(), out.data() + size_t(i) * plane, plane * sizeof(float));
+    dstDs.frame(first + i).setDepth(img);
   }
 }
 void DepthVideoProcessor::gridXformSplit(const Params& params) {   // :888-985

@@ -192,3 +192,74 @@ def test_dense_transform_kernels():
     lx = np.float32(-1.0) + np.float32(7) * (np.float32(2.0) / (np.float32(w) - np.float32(1.0))); ly = np.float32(1.0) - np.float32(3) * (np.float32(2.0) / (np.float32(h) - np.float32(1.0)))
     idx, wt = oracle.gather_spatial(cfg, lx, ly)
     np.testing.assert_allclose(wp[3, 7], [sum(sp[2 * i] * wi for i, wi in zip(idx, wt)), sum(sp[2 * i + 1] * wi for i, wi in zip(idx, wt))], rtol=1e-6, atol=1e-9)
+
+
+def test_filter_depth_sequence_through_lib_python(tmp_path):
+    """The call sequence of the reference's filter_depth (pose_optimization.py:292-326): create stream, Op.Copy,
+    Op.FlowGuidedFilter, saveDepth, save -- against the float32 restatement of the reference loop; then video.dat is re-read."""
+    import lib_python as lp
+    from oracle import host_ref
+    root = str(tmp_path / "scene")
+    N, W, H = 6, 48, 32
+    sc = synthetic.Scene(N, W, H, seed=5, motion=0.05, rot_deg=0.5)
+    synthetic_files.write_scene(sc, root)
+    v = lp.DepthVideo(); lp.DepthVideoImporter.importVideo(v, root, False)
+    v.createColorStream("down", "color_down", ".raw", CV_32FC3)
+    v.createDepthStream("depth_midas2", "depth_midas2", [-1, -1])
+    src_id = v.numDepthStreams() - 1
+    src = v.depthStream(src_id)
+    # give the frames distinct cameras and a non-trivial depth transform
+    from scipy.spatial.transform import Rotation
+    for f in range(N):
+        df = src.frame(f)
+        e = df.extrinsics; e.position = np.asarray(sc.t[f], np.float32)
+        q = Rotation.from_matrix(sc.R[f]).as_quat().astype(np.float32)
+        e.orientation = lp._makeQuat(*[float(c) for c in q])
+        df.extrinsics = e
+    proc = lp.DepthVideoProcessor(v)
+    rp = lp.DepthVideoProcessor.Params(); rp.depthStream = src_id
+    rp.depthXformDesc.type = lp.XformType.Depth; rp.depthXformDesc.depthType = lp.DepthXformType.Global; rp.depthXformDesc.valueXform = lp.ValueXformType.Scale
+    proc.resetDepthXforms(rp)
+    for f in range(N):
+        src.frame(f).depthXform().params()[0] = 1.0 / float(sc.global_scale[f])
+        src.frame(f).clearXformedCache()
+    # --- filter_depth(radius = 2) ---
+    dst_id = v.numDepthStreams()
+    v.createDepthStream(src.name() + "_filtered", "depth_midas2_filtered", [src.width(), src.height()])
+    params = lp.DepthVideoProcessor.Params()
+    assert (params.spatialRadius, params.frameRadius, params.median, params.farConnections) == (0, 2, False, False)   # lib/Processor.h:66-72
+    params.frameRange.fromString("1-5")
+    params.op = lp.DepthVideoProcessor.Op.Copy; params.sourceDepthStream = src_id; params.depthStream = dst_id
+    proc.process(params)
+    np.testing.assert_array_equal(v.depthStream(dst_id).frame(3).depth(), src.frame(3).depth())
+    params.op = lp.DepthVideoProcessor.Op.FlowGuidedFilter; params.frameRadius = 2
+    proc.process(params)
+    got = np.stack([np.array(v.depthStream(dst_id).frame(f).depth()) for f in range(1, 6)])
+    # reference loop on the same inputs (frames 0..5 are all inside the windows: base = max(0, 1 - 2) = 0)
+    depth = np.stack([np.array(src.frame(f).depth()) for f in range(N)])
+    cams = np.zeros((N, 9), np.float32)
+    for f in range(N):
+        df = src.frame(f); e = df.extrinsics
+        cams[f, :3] = e.position; cams[f, 3:7] = [e.orientation.x(), e.orientation.y(), e.orientation.z(), e.orientation.w()]
+        cams[f, 7] = df.intrinsics.hFov; cams[f, 8] = df.intrinsics.vFov
+    fwd = np.zeros((N, H, W, 2), np.float32); fwm = np.zeros((N, H, W), np.uint8); bwd = np.zeros_like(fwd); bwm = np.zeros_like(fwm)
+    import cv2
+    for f in range(N - 1):
+        fwd[f] = synthetic_files.read_raw(os.path.join(root, "flow", f"flow_{f:06d}_{f + 1:06d}.raw")); fwm[f] = cv2.imread(os.path.join(root, "flow_mask", f"mask_{f:06d}_{f + 1:06d}.png"), cv2.IMREAD_GRAYSCALE)
+        bwd[f + 1] = synthetic_files.read_raw(os.path.join(root, "flow", f"flow_{f + 1:06d}_{f:06d}.raw")); bwm[f + 1] = cv2.imread(os.path.join(root, "flow_mask", f"mask_{f + 1:06d}_{f:06d}.png"), cv2.IMREAD_GRAYSCALE)
+    want = host_ref.flow_guided_filter(depth, cams, fwd, fwm, bwd, bwm, first_out=1, num_out=5, frame_radius=2, spatial_radius=0, median=False, inv_aspect=v.invAspect())
+    np.testing.assert_allclose(got, want, rtol=1e-5)
+    assert np.abs(got - depth[1:6]).max() > 1e-4
+    # --- saveDepth + save, then re-read both ---
+    v.saveDepth(dst_id); v.save()
+    disp = synthetic_files.read_raw(os.path.join(root, "depth_midas2_filtered", "depth", "frame_000003.raw"))
+    np.testing.assert_allclose(disp, (np.float32(1.0) / got[2]).astype(np.float32), rtol=1e-6)
+    v2 = lp.DepthVideo(); v2.load(root)
+    assert v2.numFrames() == N and v2.numDepthStreams() == 2 and v2.numColorStreams() == 1 and v2.width() == v.width() and abs(v2.invAspect() - v.invAspect()) == 0
+    assert v2.depthStream(0).depthXformDesc().str() == src.depthXformDesc().str() and v2.depthStream(1).name() == "depth_midas2_filtered"
+    for f in range(N):
+        a, b = v2.depthStream(0).frame(f), src.frame(f)
+        np.testing.assert_array_equal(np.asarray(a.extrinsics.position), np.asarray(b.extrinsics.position))
+        assert list(a.depthXform().params()) == list(b.depthXform().params())
+        assert a.intrinsics.vFov == b.intrinsics.vFov
+    np.testing.assert_allclose(np.array(v2.depthStream(1).frame(3).depth()), got[2], rtol=2e-6)   # disparity round trip

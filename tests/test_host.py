@@ -64,6 +64,42 @@ def test_video_and_streams(scene_dir):
         lp.DepthVideoImporter.importVideo(lp.DepthVideo(), root + "/nope", False)
 
 
+def test_video_dat_round_trip_and_processor_defaults(scene_dir, tmp_path):
+    """video.dat written by save() (byte layout of lib/DepthVideo.cpp:300-385) is read back by load(); setDepth replaces
+    the source depth; DepthVideoProcessor.Params defaults are the reference's (lib/Processor.h:60-80)."""
+    sc, root, pairs, masks = scene_dir
+    root2 = str(tmp_path / "copy"); shutil.copytree(root, root2)
+    v = _open(root2)
+    ds = v.depthStream(0)
+    rp = lp.DepthVideoProcessor.Params(); rp.depthStream = 0; rp.depthXformDesc.parse("Grid(Scale, Linear, 4, 3, 1)")
+    lp.DepthVideoProcessor(v).resetDepthXforms(rp)
+    for f in range(8):
+        df = ds.frame(f); e = df.extrinsics; e.position = np.array([f, -f, 0.5 * f], np.float32); e.orientation = lp._makeQuat(0.0, np.sin(0.1 * f), 0.0, np.cos(0.1 * f)); df.extrinsics = e
+        df.depthXform().params()[:] = list(1.0 + 0.01 * f + 0.001 * np.arange(12))
+    v.save()
+    v2 = lp.DepthVideo(); v2.load(root2)
+    assert (v2.numFrames(), v2.numColorStreams(), v2.numDepthStreams(), v2.width(), v2.height()) == (8, 3, 1, 128, 96)
+    assert v2.aspect() == v.aspect() and v2.colorStream("down").extension() == ".raw" and v2.depthStream(0).depthXformDesc().str() == "Grid(Scale, Linear, 4, 3, 1)"
+    for f in range(8):
+        a, b = v2.depthStream(0).frame(f), ds.frame(f)
+        np.testing.assert_array_equal(a.extrinsics.position, b.extrinsics.position)
+        assert (a.extrinsics.orientation.y(), a.extrinsics.orientation.w()) == (b.extrinsics.orientation.y(), b.extrinsics.orientation.w())
+        assert (a.intrinsics.vFov, a.intrinsics.hFov) == (b.intrinsics.vFov, b.intrinsics.hFov)
+        assert list(a.depthXform().params()) == list(b.depthXform().params())
+    np.testing.assert_array_equal(v2.depthStream(0).frame(1).sourceDepth(), ds.frame(1).sourceDepth())
+    open(root2 + "/video.dat", "r+b").write(b"\x00\x00\x00\x00")
+    with pytest.raises(RuntimeError, match="magic marker"):
+        lp.DepthVideo().load(root2)
+    img = np.full((96, 128), 2.5, np.float32); ds.frame(3).setDepth(img)
+    np.testing.assert_array_equal(ds.frame(3).sourceDepth(), img)
+    with pytest.raises(RuntimeError, match="inconsistent dimensions"):
+        ds.frame(4).setDepth(np.zeros((10, 10), np.float32))
+    p = lp.DepthVideoProcessor.Params()
+    assert (p.colorStream, p.depthStream, p.sourceDepthStream, p.spatialRadius, p.frameRadius, p.median, p.farConnections) == (0, 0, 0, 0, 2, False, False)
+    assert (p.depthSigma, p.colorSigma, p.matchSeparation, p.trackSpawnDistance, p.trackPruneDistance, p.minDynamicDistance, p.minTrackLength) == (np.float32(0.3), 0.0, 10, 20, 5, 3, 4)
+    assert p.flowConsistancyThresh == np.float32(0.05)
+
+
 def test_constraints_match_numpy_cv2_restatement(scene_dir):
     import cv2
     sc, root, pairs, masks = scene_dir
