@@ -243,6 +243,33 @@ int32_t rcvd_flow_guided_filter(const rcvd_filter_params* prm, int32_t device, c
                                 const float* fwd_flow, const uint8_t* fwd_mask, const float* bwd_flow, const uint8_t* bwd_mask,
                                 const int32_t* far_pairs, const float* far_flow, const uint8_t* far_mask, float* out);
 
+/* ---- GPU flow-constraint builder ----
+ * Replaces FlowConstraintsCollection::compute (lib/FlowConstraints.cpp:401-550: admission tests, cv::cornerMinEigenVal
+ * priorities) and sampleConstraints (:352-397: greedy disc sampler) for a batch of frame pairs and frame triplets.
+ * Frames are local indices 0..num_frames-1 into color_bgr / dyn_dist.
+ *   color_bgr    [num_frames][height][width][3] f32   "down" colour stream (BGR, as cv::Mat CV_32FC3)
+ *   dyn_dist     [num_frames][dyn_height][dyn_width] f32  dynamicDistance() images (:257-286), or NULL when the video has no
+ *                dynamic_mask stream (distance = FLT_MAX)
+ *   pair_frames  [num_pairs][2], pair_flow [num_pairs][height][width][2] f32, pair_mask [num_pairs][height][width] u8
+ *   trip_frames  [num_triplets] centre frame t, trip_flow [num_triplets][2][height][width][2] (t -> t-1, t -> t+1), trip_mask likewise
+ * Outputs, in the reference's order (descending corner score; ties, which std::sort leaves unspecified, by scan index):
+ *   pair_offsets [num_pairs+1], pair_out [.][4] f32 = scaled (loc0.xy, loc1.xy)  (what flow_constraints.dat stores, :116-224)
+ *   trip_offsets [num_triplets+1], trip_out [.][6] f32 = scaled (loc0.xy, loc1.xy, loc2.xy)
+ * If a capacity (in constraints) is too small the offsets are still filled (so the caller can size the buffers) and
+ * RCVD_ERR_INVALID is returned.  Results are bit-identical to the host builder (robust_cvd_b200/host/constraints.cpp). */
+typedef struct rcvd_builder_params {
+  int32_t num_frames, width, height, dyn_width, dyn_height;
+  int32_t match_separation;        /* FlowConstraintsParams::matchSeparation */
+  int32_t num_pairs, num_triplets;
+  float min_dynamic_distance;      /* FlowConstraintsParams::minDynamicDistance */
+  float inv_aspect;                /* DepthVideo::invAspect() */
+} rcvd_builder_params;
+int32_t rcvd_build_constraints(const rcvd_builder_params* prm, int32_t device, const float* color_bgr, const float* dyn_dist,
+                               const int32_t* pair_frames, const float* pair_flow, const uint8_t* pair_mask,
+                               const int32_t* trip_frames, const float* trip_flow, const uint8_t* trip_mask,
+                               int64_t* pair_offsets, float* pair_out, int64_t pair_capacity,
+                               int64_t* trip_offsets, float* trip_out, int64_t trip_capacity);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,11 +9,14 @@ import numpy as np
 f32 = np.float32
 
 
-def pair_constraints(color_bgr, flow, mask, sep, inv_aspect):
+def pair_constraints(color_bgr, flow, mask, sep, inv_aspect, score=None):
+    """score: optional precomputed corner response (default: the real cv2.cornerMinEigenVal, whose SIMD summation order
+    differs from the C++/CUDA restatements in the last bits -- enough to swap near-equal priorities at small separations)."""
     import cv2
     h, w = mask.shape
-    gray = cv2.cvtColor(color_bgr, cv2.COLOR_BGR2GRAY)
-    score = cv2.cornerMinEigenVal(gray, 3)
+    if score is None:
+        gray = cv2.cvtColor(color_bgr, cv2.COLOR_BGR2GRAY)
+        score = cv2.cornerMinEigenVal(gray, 3)
     iy, ix = np.mgrid[0:h, 0:w]
     fx1 = (ix.astype(f32) + flow[..., 0]).astype(f32); fy1 = (iy.astype(f32) + flow[..., 1]).astype(f32)
     ix1 = (fx1 + f32(0.5)).astype(np.int32); iy1 = (fy1 + f32(0.5)).astype(np.int32)      # C (int): truncation toward zero

@@ -74,6 +74,12 @@ class FilterParams(C.Structure):
                                          "frame_radius", "spatial_radius", "median", "num_far")] + [("inv_aspect", C.c_float)]
 
 
+class BuilderParams(C.Structure):
+    """rcvd_builder_params (include/rcvd.h)."""
+    _fields_ = [(n, C.c_int32) for n in ("num_frames", "width", "height", "dyn_width", "dyn_height", "match_separation", "num_pairs", "num_triplets")] + \
+               [("min_dynamic_distance", C.c_float), ("inv_aspect", C.c_float)]
+
+
 def default_config(num_frames, aspect, **kw):
     """Config with the reference's Params defaults (lib/PoseOptimizer.h:55-103)."""
     focal_long = kw.pop("focal_long", 0.3461538376301239)

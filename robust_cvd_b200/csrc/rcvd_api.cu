@@ -21,6 +21,7 @@
 #include "rcvd_linalg.cuh"
 #include "rcvd_dense.cuh"
 #include "rcvd_filter.cuh"
+#include "rcvd_builder.cuh"
 static int64_t g_filter_launches = 0;
 
 using namespace rcvd;
@@ -1314,3 +1315,116 @@ RCVD_API int32_t rcvd_flow_guided_filter(const rcvd_filter_params* prm, int32_t 
   return rc;
 }
 RCVD_API int64_t rcvd_filter_launch_count() { return g_filter_launches; }
+
+// ---------------------------------------------------------------------------
+// GPU flow-constraint builder (rcvd_builder.cuh)
+// ---------------------------------------------------------------------------
+static int64_t g_builder_launches = 0, g_builder_rounds = 0;
+RCVD_API int64_t rcvd_builder_launch_count() { return g_builder_launches; }
+RCVD_API int64_t rcvd_builder_last_rounds() { return g_builder_rounds; }
+RCVD_API int32_t rcvd_build_constraints(const rcvd_builder_params* prm, int32_t device, const float* color_bgr, const float* dyn_dist,
+                                        const int32_t* pair_frames, const float* pair_flow, const uint8_t* pair_mask,
+                                        const int32_t* trip_frames, const float* trip_flow, const uint8_t* trip_mask,
+                                        int64_t* pair_offsets, float* pair_out, int64_t pair_capacity,
+                                        int64_t* trip_offsets, float* trip_out, int64_t trip_capacity) {
+  if (!prm || !color_bgr) return set_err(RCVD_ERR_INVALID, "null argument");
+  const rcvd_builder_params& q = *prm;
+  const int P = q.num_pairs, T = q.num_triplets, F = q.num_frames, I = P + T;
+  if (F <= 0 || q.width <= 0 || q.height <= 0 || P < 0 || T < 0 || q.match_separation < 0 || !(q.inv_aspect > 0.f)) return set_err(RCVD_ERR_INVALID, "bad builder parameters");
+  if ((P > 0 && (!pair_frames || !pair_flow || !pair_mask || !pair_offsets)) || (T > 0 && (!trip_frames || !trip_flow || !trip_mask || !trip_offsets)))
+    return set_err(RCVD_ERR_INVALID, "null argument");
+  if (dyn_dist && (q.dyn_width <= 0 || q.dyn_height <= 0)) return set_err(RCVD_ERR_INVALID, "bad dynamic-distance size");
+  for (int i = 0; i < P; ++i) if (pair_frames[2 * i] < 0 || pair_frames[2 * i] >= F || pair_frames[2 * i + 1] < 0 || pair_frames[2 * i + 1] >= F) return set_err(RCVD_ERR_INVALID, "pair %d out of range", i);
+  for (int i = 0; i < T; ++i) if (trip_frames[i] < 1 || trip_frames[i] >= F) return set_err(RCVD_ERR_INVALID, "triplet %d out of range", i);
+  if (pair_offsets) pair_offsets[0] = 0;
+  if (trip_offsets) trip_offsets[0] = 0;
+  if (I == 0) return RCVD_OK;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev)
+    return set_err(RCVD_ERR_NO_DEVICE, "no usable CUDA device (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device ordinal out of range");
+  CK(cudaSetDevice(device));
+  const size_t plane = (size_t)q.width * q.height, FP = plane * F;
+  cudaStream_t st; CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  std::vector<void*> bufs; bool ok = true;
+  auto dev = [&](size_t bytes) -> void* { void* ptr = nullptr; if (cudaMallocAsync(&ptr, std::max<size_t>(bytes, 16), st) != cudaSuccess) { ok = false; return nullptr; } bufs.push_back(ptr); return ptr; };
+  auto up = [&](const void* src, size_t bytes) -> void* { void* d = dev(bytes); if (d && src && bytes) cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st); return d; };
+  auto cleanup = [&]() { for (void* b : bufs) cudaFreeAsync(b, st); cudaStreamSynchronize(st); cudaStreamDestroy(st); };
+  // ---- corner scores of every frame ----
+  float* d_bgr = (float*)up(color_bgr, FP * 3 * sizeof(float));
+  float* d_gray = (float*)dev(FP * 4), *d_pl = (float*)dev(FP * 12), *d_tmp = (float*)dev(FP * 12), *d_corner = (float*)dev(FP * 4);
+  BuilderArgs a{};
+  a.dyn = dyn_dist ? (const float*)up(dyn_dist, (size_t)F * q.dyn_width * q.dyn_height * 4) : nullptr;
+  a.pair_frames = (const int*)up(pair_frames, (size_t)P * 8); a.pair_flow = (const float*)up(pair_flow, (size_t)P * plane * 8); a.pair_mask = (const uint8_t*)up(pair_mask, (size_t)P * plane);
+  a.trip_frames = (const int*)up(trip_frames, (size_t)T * 4); a.trip_flow = (const float*)up(trip_flow, (size_t)T * 2 * plane * 8); a.trip_mask = (const uint8_t*)up(trip_mask, (size_t)T * 2 * plane);
+  a.prio = (float*)dev((size_t)I * plane * 4); a.state = (uint8_t*)dev((size_t)I * plane);
+  unsigned long long* d_cnt = (unsigned long long*)dev((size_t)(2 * I + 2) * 8);   // [0] undecided, [1..I] counts / offsets, [I+1..2I] cursors
+  if (!ok) { cleanup(); return set_err(RCVD_ERR_CUDA, "device allocation failed in rcvd_build_constraints"); }
+  const int W = q.width, H = q.height;
+  k_gray<<<(unsigned)((FP + 255) / 256), 256, 0, st>>>(d_bgr, d_gray, FP);
+  k_sobel_products<<<(unsigned)((FP + 255) / 256), 256, 0, st>>>(d_gray, d_pl, F, H, W);
+  k_box_h<<<(unsigned)((FP * 3 + 255) / 256), 256, 0, st>>>(d_pl, d_tmp, (size_t)3 * F * H, W);
+  k_box_v_eig<<<(unsigned)((FP + 255) / 256), 256, 0, st>>>(d_tmp, d_corner, F, H, W);
+  g_builder_launches += 4;
+  a.corner = d_corner; a.P = P; a.T = T; a.h = H; a.w = W; a.dh = q.dyn_height; a.dw = q.dyn_width; a.sep = q.match_separation; a.min_dyn = q.min_dynamic_distance;
+  // dynamic-mask scale (lib/FlowConstraints.cpp:415-417); without a dynamic mask the distance image has the colour size (:277-285)
+  a.dsx = dyn_dist ? q.dyn_width / float(W) : 1.f; a.dsy = dyn_dist ? q.dyn_height / float(H) : 1.f;
+  a.sx = 1.f / W; a.sy = q.inv_aspect / H;
+  const unsigned gx = (unsigned)((plane + 255) / 256);
+  if (P > 0) { k_pair_candidates<<<dim3(gx, P), 256, 0, st>>>(a); g_builder_launches++; }
+  if (T > 0) { k_triplet_candidates<<<dim3(gx, T), 256, 0, st>>>(a); g_builder_launches++; }
+  // ---- selection rounds until nothing is undecided ----
+  int rounds = 0;
+  for (;;) {
+    cudaMemsetAsync(d_cnt, 0, 8, st);
+    k_select_round<<<dim3(gx, I), 256, 0, st>>>(a, d_cnt); g_builder_launches++; ++rounds;
+    unsigned long long und = 0;
+    e = cudaMemcpyAsync(&und, d_cnt, 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { cleanup(); return set_err(RCVD_ERR_CUDA, "constraint selection failed: %s", cudaGetErrorString(e)); }
+    if (und == 0) break;
+    if (rounds > 4 * (W + H) + 16) { cleanup(); return set_err(RCVD_ERR_CUDA, "constraint selection did not converge"); }
+  }
+  g_builder_rounds = rounds;
+  // ---- counts, offsets, emission ----
+  cudaMemsetAsync(d_cnt, 0, (size_t)(2 * I + 2) * 8, st);
+  k_count_accepted<<<dim3(gx, I), 256, 0, st>>>(a, d_cnt + 1); g_builder_launches++;
+  std::vector<unsigned long long> cnt(I), off(I + 1, 0);
+  CK(cudaMemcpyAsync(cnt.data(), d_cnt + 1, (size_t)I * 8, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+  for (int i = 0; i < I; ++i) off[i + 1] = off[i] + cnt[i];
+  const unsigned long long pair_total = off[P], total = off[I];
+  for (int i = 0; i < P; ++i) pair_offsets[i + 1] = (int64_t)off[i + 1];
+  for (int i = 0; i < T; ++i) trip_offsets[i + 1] = (int64_t)(off[P + i + 1] - pair_total);
+  if ((int64_t)pair_total > pair_capacity || (int64_t)(total - pair_total) > trip_capacity || (pair_total > 0 && !pair_out) || (total > pair_total && !trip_out)) {
+    cleanup(); return set_err(RCVD_ERR_INVALID, "output capacity too small: %llu pair and %llu triplet constraints", pair_total, total - pair_total);
+  }
+  int rc = RCVD_OK;
+  if (total > 0) {
+    unsigned long long* d_off = (unsigned long long*)up(off.data(), (size_t)(I + 1) * 8);
+    int* d_idx = (int*)dev(total * 4); float* d_score = (float*)dev(total * 4);
+    float* d_po = (float*)dev(std::max<size_t>(pair_total, 1) * 16); float* d_to = (float*)dev(std::max<size_t>(total - pair_total, 1) * 24);
+    if (!ok) { cleanup(); return set_err(RCVD_ERR_CUDA, "device allocation failed in rcvd_build_constraints"); }
+    k_emit<<<dim3(gx, I), 256, 0, st>>>(a, d_off, d_cnt + 1 + I, d_idx, d_score, d_po, d_to, pair_total); g_builder_launches++;
+    std::vector<int> idx(total); std::vector<float> score(total), po(pair_total * 4), to((total - pair_total) * 6);
+    cudaMemcpyAsync(idx.data(), d_idx, total * 4, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(score.data(), d_score, total * 4, cudaMemcpyDeviceToHost, st);
+    if (pair_total) cudaMemcpyAsync(po.data(), d_po, pair_total * 16, cudaMemcpyDeviceToHost, st);
+    if (total > pair_total) cudaMemcpyAsync(to.data(), d_to, (total - pair_total) * 24, cudaMemcpyDeviceToHost, st);
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = set_err(RCVD_ERR_CUDA, "constraint emission failed: %s", cudaGetErrorString(e));
+    else {
+      // order each item's survivors by priority (host: a few hundred entries per item)
+      std::vector<unsigned long long> perm;
+      for (int i = 0; i < I; ++i) {
+        const unsigned long long b = off[i], n = cnt[i];
+        perm.resize(n); for (unsigned long long k = 0; k < n; ++k) perm[k] = b + k;
+        std::sort(perm.begin(), perm.end(), [&](unsigned long long x, unsigned long long y) { return score[x] > score[y] || (score[x] == score[y] && idx[x] < idx[y]); });
+        for (unsigned long long k = 0; k < n; ++k) {
+          if (i < P) std::memcpy(pair_out + (b + k) * 4, po.data() + perm[k] * 4, 16);
+          else std::memcpy(trip_out + (b - pair_total + k) * 6, to.data() + (perm[k] - pair_total) * 6, 24);
+        }
+      }
+    }
+  }
+  cleanup();
+  return rc;
+}

@@ -1,13 +1,17 @@
 // constraints.cpp -- FlowConstraintsCollection (reference lib/FlowConstraints.cpp) and the OpenCV
 // image operators it relies on, restated (cvtColor BGR2GRAY, cornerMinEigenVal(blockSize 3),
-// distanceTransform(DIST_L2, 5)).  CPU host code: runs once per fine-tune and is cached in
-// flow_constraints.dat; a GPU builder is SURVEY.md section 8f-2 ("next").
+// distanceTransform(DIST_L2, 5)).  Two builders produce identical lists: the GPU builder (default; rcvd_build_constraints,
+// csrc/rcvd_builder.cuh) and the sequential host builder below, which is the reference's own CPU
+// stage restated and is selected explicitly with RCVD_CONSTRAINT_BUILDER=host (no automatic fallback: without a CUDA
+// device the default builder fails).
 #include "model.h"
 
 #include <algorithm>
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 #include <fstream>
 #include <sstream>
 #include <stdexcept>
@@ -191,8 +195,13 @@ Image FlowConstraintsCollection::dynamicDistance(int frame) {   // :257-286
 }
 void FlowConstraintsCollection::compute() {
   logInfo("Computing constraints...");
-  for (auto& kv : pairs_) compute(kv.first);
-  for (auto& kv : triplets_) computeTriplet(kv.first);
+  const char* sel = std::getenv("RCVD_CONSTRAINT_BUILDER");
+  if (sel && std::string(sel) == "host") {
+    for (auto& kv : pairs_) compute(kv.first);
+    for (auto& kv : triplets_) computeTriplet(kv.first);
+  } else if (!sel || std::string(sel) == "gpu" || std::string(sel).empty()) {
+    computeOnDevice();
+  } else throw std::runtime_error("RCVD_CONSTRAINT_BUILDER must be 'gpu' or 'host'.");
 }
 
 namespace {
@@ -215,7 +224,7 @@ FlowMask loadFlowAndMask(DepthVideo& video, const std::string& path, int a, int 
 template <class C, int REF> void sampleConstraints(DepthVideo& video, int sep, std::vector<Pixel<C>>& pixels, std::vector<C>& output, int nobs) {
   ColorStream& cs = video.colorStream("down");
   const int w = cs.width(), h = cs.height();
-  std::sort(pixels.begin(), pixels.end());
+  std::stable_sort(pixels.begin(), pixels.end());   // the reference's std::sort leaves equal scores unordered; scan order breaks ties here and on the GPU
   std::vector<uint8_t> invalid(size_t(w) * h, 0);
   const int size = 2 * sep + 1;
   std::vector<uint8_t> disk(size_t(size) * size);
@@ -300,6 +309,91 @@ void FlowConstraintsCollection::computeTriplet(int triplet) {   // :467-550 (qui
     }
   }
   sampleConstraints<TripletConstraint, 1>(*video_, params_.matchSeparation, pixels, triplets_.at(triplet), 3);
+}
+
+// All pairs and triplets through rcvd_build_constraints, in batches that bound the host staging memory.
+void FlowConstraintsCollection::computeOnDevice() {
+  ColorStream& cs = video_->colorStream("down");
+  const int w = cs.width(), h = cs.height();
+  if (w <= 0 || h <= 0) throw std::runtime_error("Missing color frame.");
+  const size_t plane = size_t(w) * h;
+  // frames referenced by any item -> local indices
+  std::map<int, int> local;
+  for (auto& kv : pairs_) { local[kv.first.first] = 0; local[kv.first.second] = 0; }
+  std::vector<int> trips;
+  for (auto& kv : triplets_) {
+    const int t = kv.first;
+    if (!fileExists(pairName("%s/flow/flow_%06d_%06d.raw", path_, t, t - 1)) || !fileExists(pairName("%s/flow/flow_%06d_%06d.raw", path_, t, t + 1))) continue;
+    trips.push_back(t); local[t - 1] = 0; local[t] = 0; local[t + 1] = 0;
+  }
+  if (local.empty()) return;
+  int F = 0; for (auto& kv : local) kv.second = F++;
+  std::vector<float> color(size_t(F) * plane * 3), dyn;
+  const bool hasDyn = video_->hasColorStream("dynamic_mask");
+  int dw = 0, dh = 0;
+  for (auto& kv : local) {
+    const Image* img = cs.frame(kv.first).image();
+    if (!img) throw std::runtime_error("Missing color frame.");
+    if (img->cols != w || img->rows != h || img->type != cvMakeType(CV_32F, 3)) throw std::runtime_error("Color frame has the wrong size or type.");
+    std::memcpy(color.data() + size_t(kv.second) * plane * 3, img->ptr<float>(), plane * 3 * sizeof(float));
+    if (hasDyn) {
+      Image dd = dynamicDistance(kv.first);
+      if (dyn.empty()) { dw = dd.cols; dh = dd.rows; dyn.resize(size_t(F) * dw * dh); }
+      if (dd.cols != dw || dd.rows != dh) throw std::runtime_error("Dynamic masks have inconsistent dimensions.");
+      std::memcpy(dyn.data() + size_t(kv.second) * dw * dh, dd.ptr<float>(), size_t(dw) * dh * sizeof(float));
+    }
+  }
+  rcvd_builder_params prm{};
+  prm.num_frames = F; prm.width = w; prm.height = h; prm.dyn_width = dw; prm.dyn_height = dh; prm.match_separation = params_.matchSeparation;
+  prm.min_dynamic_distance = params_.minDynamicDistance; prm.inv_aspect = video_->invAspect();
+  const size_t kBatchBytes = size_t(768) << 20;   // staging budget per call
+  const size_t perPair = plane * 9, perTrip = plane * 18;
+  std::vector<PairKey> keys; for (auto& kv : pairs_) keys.push_back(kv.first);
+  size_t pi = 0, ti = 0;
+  while (pi < keys.size() || ti < trips.size()) {
+    const size_t np = std::min(keys.size() - pi, std::max<size_t>(1, kBatchBytes / perPair));
+    const size_t budgetLeft = kBatchBytes > np * perPair ? kBatchBytes - np * perPair : 0;
+    const size_t nt = pi + np >= keys.size() ? std::min(trips.size() - ti, std::max<size_t>(np == 0 ? 1 : 0, budgetLeft / perTrip)) : 0;
+    std::vector<int32_t> pf(np * 2), tf(nt);
+    std::vector<float> pflow(np * plane * 2), tflow(nt * 2 * plane * 2);
+    std::vector<uint8_t> pmask(np * plane), tmask(nt * 2 * plane);
+    for (size_t k = 0; k < np; ++k) {
+      const PairKey& key = keys[pi + k];
+      FlowMask fm = loadFlowAndMask(*video_, path_, key.first, key.second);
+      pf[2 * k] = local[key.first]; pf[2 * k + 1] = local[key.second];
+      std::memcpy(pflow.data() + k * plane * 2, fm.flow.ptr<float>(), plane * 2 * sizeof(float)); std::memcpy(pmask.data() + k * plane, fm.mask.ptr<uint8_t>(), plane);
+    }
+    for (size_t k = 0; k < nt; ++k) {
+      const int t = trips[ti + k]; tf[k] = local[t];
+      if (local[t - 1] != local[t] - 1) throw std::runtime_error("Triplet frames must be consecutive in the constraint frame range.");
+      for (int s2 = 0; s2 < 2; ++s2) {
+        FlowMask fm = loadFlowAndMask(*video_, path_, t, s2 == 0 ? t - 1 : t + 1);
+        std::memcpy(tflow.data() + (k * 2 + s2) * plane * 2, fm.flow.ptr<float>(), plane * 2 * sizeof(float)); std::memcpy(tmask.data() + (k * 2 + s2) * plane, fm.mask.ptr<uint8_t>(), plane);
+      }
+    }
+    prm.num_pairs = int(np); prm.num_triplets = int(nt);
+    std::vector<int64_t> poff(np + 1, 0), toff(nt + 1, 0);
+    const int sep = std::max(1, params_.matchSeparation);
+    int64_t pcap = int64_t(np) * int64_t(std::min<size_t>(plane, 4 * plane / (size_t(sep) * sep) + 64)), tcap = int64_t(nt) * int64_t(std::min<size_t>(plane, 4 * plane / (size_t(sep) * sep) + 64));
+    std::vector<float> pout, tout;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      pout.resize(size_t(pcap) * 4); tout.resize(size_t(tcap) * 6);
+      const int rc = rcvd_build_constraints(&prm, 0, color.data(), hasDyn ? dyn.data() : nullptr, pf.data(), pflow.data(), pmask.data(), tf.data(), tflow.data(), tmask.data(),
+                                            poff.data(), pout.data(), pcap, toff.data(), tout.data(), tcap);
+      if (rc == RCVD_OK) break;
+      if (attempt == 0 && (poff[np] > pcap || toff[nt] > tcap)) { pcap = poff[np]; tcap = toff[nt]; continue; }   // sizes are known now
+      throw std::runtime_error(std::string("GPU constraint builder failed: ") + rcvd_last_error());
+    }
+    for (size_t k = 0; k < np; ++k) {
+      std::vector<PairConstraint>& out = pairs_.at(keys[pi + k]); out.clear(); out.resize(size_t(poff[k + 1] - poff[k]));
+      for (size_t c = 0; c < out.size(); ++c) { std::memcpy(out[c].loc, pout.data() + (size_t(poff[k]) + c) * 4, 16); out[c].isStatic = true; }
+    }
+    for (size_t k = 0; k < nt; ++k) {
+      std::vector<TripletConstraint>& out = triplets_.at(trips[ti + k]); out.clear(); out.resize(size_t(toff[k + 1] - toff[k]));
+      for (size_t c = 0; c < out.size(); ++c) { std::memcpy(out[c].loc, tout.data() + (size_t(toff[k]) + c) * 6, 24); out[c].isStatic = true; }
+    }
+    pi += np; ti += nt;
+  }
 }
 
 void FlowConstraintsCollection::resetStaticFlag() {

@@ -147,6 +147,14 @@ PYBIND11_MODULE(lib_python, m) {
           for (size_t i = 0; i < kv.second.size(); ++i) { std::memcpy(a.mutable_data() + 4 * i, kv.second[i].loc, 16); s.mutable_data()[i] = kv.second[i].isStatic; }
           d[py::make_tuple(kv.first.first, kv.first.second)] = py::make_tuple(a, s);
         }
+        return d; })
+      .def("_triplets", [](const FlowConstraintsCollection& c) {
+        py::dict d;
+        for (const auto& kv : c.triplets()) {
+          py::array_t<float> a({(py::ssize_t)kv.second.size(), (py::ssize_t)6}); py::array_t<bool> s((py::ssize_t)kv.second.size());
+          for (size_t i = 0; i < kv.second.size(); ++i) { std::memcpy(a.mutable_data() + 6 * i, kv.second[i].loc, 24); s.mutable_data()[i] = kv.second[i].isStatic; }
+          d[py::int_(kv.first)] = py::make_tuple(a, s);
+        }
         return d; });
 
   struct DepthVideoImporter {};

@@ -263,7 +263,8 @@ class FlowConstraintsCollection {
   void pruneStaticFlag(int distance);
   const std::map<PairKey, std::vector<PairConstraint>>& pairs() const { return pairs_; }
   const std::map<int, std::vector<TripletConstraint>>& triplets() const { return triplets_; }
-  void compute();
+  void compute();                       // GPU builder (rcvd_build_constraints) unless RCVD_CONSTRAINT_BUILDER=host
+  void computeOnDevice();
   void compute(const PairKey& pair);
   void computeTriplet(int triplet);
  private:

@@ -239,6 +239,36 @@ def flow_guided_filter(depth, cams, fwd_flow, fwd_mask, bwd_flow, bwd_mask, firs
     return out
 
 
+def build_constraints(color_bgr, pair_frames, pair_flow, pair_mask, match_separation, inv_aspect, dyn_dist=None, min_dynamic_distance=-1.0,
+                      trip_frames=None, trip_flow=None, trip_mask=None, device=0):
+    """rcvd_build_constraints (FlowConstraintsCollection::compute + sampleConstraints, reference lib/FlowConstraints.cpp:352-550) on the GPU.
+    Returns (pair_offsets, pair_constraints [n,4], trip_offsets, trip_constraints [m,6])."""
+    color = np.ascontiguousarray(color_bgr, np.float32)
+    F, h, w = color.shape[:3]
+    pf = np.ascontiguousarray(pair_frames, np.int32).reshape(-1, 2); P = len(pf)
+    pfl = np.ascontiguousarray(pair_flow, np.float32) if P else None; pm = np.ascontiguousarray(pair_mask, np.uint8) if P else None
+    T = 0 if trip_frames is None else len(trip_frames)
+    tf = np.ascontiguousarray(trip_frames, np.int32) if T else None
+    tfl = np.ascontiguousarray(trip_flow, np.float32) if T else None; tm = np.ascontiguousarray(trip_mask, np.uint8) if T else None
+    dd = None if dyn_dist is None else np.ascontiguousarray(dyn_dist, np.float32)
+    prm = abi.BuilderParams(num_frames=F, width=w, height=h, dyn_width=0 if dd is None else dd.shape[2], dyn_height=0 if dd is None else dd.shape[1],
+                            match_separation=match_separation, num_pairs=P, num_triplets=T, min_dynamic_distance=min_dynamic_distance, inv_aspect=inv_aspect)
+    poff = np.zeros(P + 1, np.int64); toff = np.zeros(T + 1, np.int64)
+    pcap, tcap = 0, 0
+    for attempt in range(2):
+        pout = np.zeros((max(pcap, 1), 4), np.float32); tout = np.zeros((max(tcap, 1), 6), np.float32)
+        rc = lib().rcvd_build_constraints(C.byref(prm), C.c_int32(device), _p(color, C.c_float), _p(dd, C.c_float), _p(pf if P else None, C.c_int32), _p(pfl, C.c_float), _p(pm, C.c_uint8),
+                                          _p(tf, C.c_int32), _p(tfl, C.c_float), _p(tm, C.c_uint8), _p(poff, C.c_int64), _p(pout, C.c_float), C.c_int64(pcap),
+                                          _p(toff, C.c_int64), _p(tout, C.c_float), C.c_int64(tcap))
+        if rc == 0:
+            break
+        if attempt == 0 and (poff[P] > pcap or toff[T] > tcap):
+            pcap, tcap = int(poff[P]), int(toff[T])      # the first call reports the sizes
+            continue
+        _check(rc)
+    return poff, pout[:poff[P]], toff, tout[:toff[T]]
+
+
 def fp64_tensor_peak(device=0):
     """Bench hook: live-measured fp64 tensor-core (DMMA) peak of `device` in TFLOP/s."""
     v = C.c_double()

@@ -19,6 +19,13 @@ from oracle import host_ref  # noqa: E402
 CV_32FC3, CV_8UC1 = 21, 0
 
 
+@pytest.fixture(autouse=True)
+def _host_constraint_builder(monkeypatch):
+    """These tests run without a GPU: select the sequential host builder explicitly (the default is the GPU builder,
+    tests/test_gpu_builder.py checks that both produce identical lists)."""
+    monkeypatch.setenv("RCVD_CONSTRAINT_BUILDER", "host")
+
+
 @pytest.fixture(scope="module")
 def scene_dir(tmp_path_factory):
     root = str(tmp_path_factory.mktemp("scene8"))
