@@ -22,5 +22,15 @@ int main() {
     printf("rep %d: %.1f us; cycles: load %lld, first chol %lld, panel(thread0) %lld, wait-panel %lld, update-to-lookahead %lld, lookahead chol %lld, rest of update %lld, wait-update %lld  (%s)\n",
            rep, ms * 1e3, ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6], ph[7], cudaGetErrorString(cudaGetLastError()));
   }
+  // correctness: compare with a plain host Cholesky
+  std::vector<double> Lh = A, Ld((size_t)n * n);
+  for (int j = 0; j < n; ++j) {
+    double d = Lh[(size_t)j * n + j]; for (int k = 0; k < j; ++k) d -= Lh[(size_t)j * n + k] * Lh[(size_t)j * n + k];
+    d = std::sqrt(d); Lh[(size_t)j * n + j] = d;
+    for (int i = j + 1; i < n; ++i) { double v = Lh[(size_t)i * n + j]; for (int k = 0; k < j; ++k) v -= Lh[(size_t)i * n + k] * Lh[(size_t)j * n + k]; Lh[(size_t)i * n + j] = v / d; }
+  }
+  cudaMemcpy(Ld.data(), dA, Ld.size() * 8, cudaMemcpyDeviceToHost);
+  double err = 0; for (int i = 0; i < n; ++i) for (int j = 0; j <= i; ++j) err = std::max(err, std::fabs(Ld[(size_t)i * n + j] - Lh[(size_t)i * n + j]));
+  printf("max |L_gpu - L_host| = %.3e\n", err);
   return 0;
 }
