@@ -178,6 +178,9 @@ int32_t rcvd_problem_set_triplets(rcvd_problem* p, int32_t num_groups, const int
  * unique_id is the 128-byte ncclUniqueId (rcvd_nccl_unique_id on rank 0). */
 int32_t rcvd_nccl_unique_id(uint8_t out[128]);
 int32_t rcvd_problem_init_comm(rcvd_problem* p, int32_t nranks, int32_t rank, const uint8_t unique_id[128]);
+/* Multi-GPU: the GLOBAL list of directed frame pairs [num_pairs][2] (all ranks pass the same list) so that every rank builds
+ * the identical block structure / elimination order although it only holds a shard of the constraints. */
+int32_t rcvd_problem_set_structure(rcvd_problem* p, int32_t num_pairs, const int32_t* pair_frames);
 /* regulariser terms are evaluated by the rank that owns frame f: f % nranks == rank */
 
 /* State: params[N * stride] host doubles. */

@@ -1,0 +1,39 @@
+/* rcvd_hooks.h -- test / bench hooks exported by librcvd_b200.so.  NOT part of the drop-in boundary (include/rcvd.h):
+ * nothing in the reference corresponds to these; tests/, bench.py and tools/ use them to look inside the solver. */
+#ifndef RCVD_HOOKS_H_
+#define RCVD_HOOKS_H_
+#include "rcvd.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* kernels launched so far by this handle / by the filter / by the constraint builder (the "did the CUDA path run" evidence) */
+int64_t rcvd_launch_count(rcvd_problem* p);
+int64_t rcvd_filter_launch_count(void);
+int64_t rcvd_builder_launch_count(void);
+int64_t rcvd_builder_last_rounds(void);          /* selection rounds of the last rcvd_build_constraints call */
+
+/* {frames, off-diagonal factor blocks, levels, H blocks, npad, stride, tiles, update tasks} */
+int32_t rcvd_structure_info(rcvd_problem* p, int32_t out[8]);
+
+/* y = (S H S + diag(D2))^-1 b with the current H (exercises factorisation + substitution alone) */
+int32_t rcvd_debug_linear_solve(rcvd_problem* p, const double* S, const double* D2, const double* b, double* y);
+
+/* per-kernel-class device time of one factorisation + solve: out_ms[0..5] = load, potrf, trinv, trsm, update GEMM,
+ * substitution; [6] = update-GEMM launches, [7] = their algorithmic flops.  reps > 0: serialised on one stream;
+ * reps < 0: two-stream overlap kept, main-stream view. */
+int32_t rcvd_debug_profile_linear(rcvd_problem* p, int32_t reps, double out_ms[8]);
+/* fp64 tensor-core (DMMA) peak of the device in TFLOP/s, measured live */
+int32_t rcvd_debug_fp64_tensor_peak(int32_t device, double* tflops);
+
+/* A/B switches (defaults in parentheses) */
+int32_t rcvd_debug_set_fast_path(rcvd_problem* p, int32_t on);        /* (1) specialised accumulate kernel */
+int32_t rcvd_debug_set_overlap(rcvd_problem* p, int32_t on);          /* (1) two-stream factorisation graph */
+int32_t rcvd_debug_set_trsm_ll(rcvd_problem* p, int32_t on);          /* (1) left-looking tensor-core TRSM */
+int32_t rcvd_debug_set_order_slack(rcvd_problem* p, int32_t slack);   /* (3) multiple-elimination degree slack; -1 greedy */
+int32_t rcvd_debug_set_side_slice(rcvd_problem* p, int32_t ctas);     /* (0) grid cap of one overlapped update launch */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RCVD_HOOKS_H_ */

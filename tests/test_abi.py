@@ -8,8 +8,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared():
-    txt = open(os.path.join(ROOT, "include", "rcvd.h")).read()
+def _declared(header="rcvd.h"):
+    txt = open(os.path.join(ROOT, "include", header)).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     return sorted(set(re.findall(r"\b(rcvd_[a-z_0-9]+)\s*\(", txt)))
 
@@ -21,6 +21,20 @@ def test_library_exports_declared_symbols():
     assert len(names) >= 20
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/rcvd.h but not exported"
+
+
+def test_every_exported_symbol_is_declared_in_a_header():
+    """include/rcvd.h is the boundary, include/rcvd_hooks.h the test/bench hooks: nothing else is exported."""
+    import subprocess
+    from robust_cvd_b200 import solver
+    solver.lib()
+    so = os.path.join(ROOT, "robust_cvd_b200", "librcvd_b200.so")
+    out = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True).stdout
+    exported = sorted({ln.split()[-1] for ln in out.splitlines() if " T rcvd_" in ln})
+    declared = set(_declared("rcvd.h")) | set(_declared("rcvd_hooks.h"))
+    assert exported and not [n for n in exported if n not in declared]
+    for n in _declared("rcvd_hooks.h"):
+        assert n in exported, f"{n} declared in include/rcvd_hooks.h but not exported"
 
 
 def test_struct_layouts_and_strides():
