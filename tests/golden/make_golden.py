@@ -44,7 +44,54 @@ def golden_solver():
     np.savez_compressed(os.path.join(HERE, "oracle_solver_golden.npz"), **out)
 
 
+def golden_raw_images():
+    """.raw wire format: files written by the reference's own utils/image_io.py::save_raw_float32_image (imported unchanged)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_image_io", "/root/reference/utils/image_io.py")
+    io = importlib.util.module_from_spec(spec)
+    try:
+        spec.loader.exec_module(io)
+    except Exception:      # the module imports cv2 / other helpers at the top; only the two raw functions are needed
+        src = open("/root/reference/utils/image_io.py").read()
+        a = src.index("def load_raw_float32_image"); b = src.index("def save_raw_float32_image")
+        end = src.find("\ndef ", b + 10)
+        ns = {"np": np, "struct": __import__("struct")}
+        exec(compile(src[a:end if end > 0 else len(src)], "/root/reference/utils/image_io.py", "exec"), ns)      # executed in place, not copied
+        io = type("io", (), {k: staticmethod(v) for k, v in ns.items() if callable(v)})
+    rng = np.random.default_rng(4)
+    disp = (rng.random((5, 7)) * 2 + 0.1).astype(np.float32); disp[1, 2] = 0.0; disp[3, 3] = np.inf
+    flow = rng.normal(0, 1.5, (5, 7, 2)).astype(np.float32)
+    color = rng.random((5, 7, 3)).astype(np.float32)
+    io.save_raw_float32_image(os.path.join(HERE, "ref_writer_disparity_5x7.raw"), disp)
+    io.save_raw_float32_image(os.path.join(HERE, "ref_writer_flow_5x7x2.raw"), flow)
+    io.save_raw_float32_image(os.path.join(HERE, "ref_writer_color_5x7x3.raw"), color)
+    np.savez_compressed(os.path.join(HERE, "ref_writer_arrays.npz"), disp=disp, flow=flow, color=color)
+
+
+def golden_host_restatements():
+    """Outputs of the float32 restatements of the post-filter and the disc sampler (oracle/host_ref.py) on fixed inputs:
+    pins the restatements against silent edits (the reference's C++ for these cannot be built here)."""
+    from oracle import host_ref
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from tests.test_gpu_filter import make_filter_case
+    case, far_pairs, ff, fm = make_filter_case(F=5, w=20, h=12, seed=9, far=((2, 0), (2, 4)))
+    out = {}
+    for name, kw in (("mean_r0", dict(spatial_radius=0, median=False)), ("median_r1_far", dict(spatial_radius=1, median=True, far_pairs=far_pairs, far_flow=ff, far_mask=fm))):
+        out["filter_" + name] = host_ref.flow_guided_filter(**case, first_out=1, num_out=3, frame_radius=2, **kw)
+    rng = np.random.default_rng(12)
+    iy, ix = np.mgrid[0:24, 0:32]
+    color = (np.sin(ix * 0.9)[..., None] * np.cos(iy * 0.7)[..., None] * 0.4 + 0.5 + rng.normal(0, 0.08, (24, 32, 3))).astype(np.float32)
+    flow = rng.normal(0, 2.0, (24, 32, 2)).astype(np.float32); mask = (rng.random((24, 32)) > 0.1).astype(np.uint8) * 255
+    for sep in (1, 4):
+        c, score = host_ref.pair_constraints(color, flow, mask, sep, np.float32(0.75))
+        out[f"sampler_sep{sep}"] = c
+    out["sampler_color"] = color; out["sampler_flow"] = flow; out["sampler_mask"] = mask; out["sampler_score"] = score
+    np.savez_compressed(os.path.join(HERE, "host_restatement_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     golden_pairs()
     golden_solver()
+    golden_raw_images()
+    golden_host_restatements()
     print("golden fixtures written")

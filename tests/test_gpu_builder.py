@@ -87,6 +87,14 @@ def test_gpu_builder_equals_host_builder_through_lib_python(tmp_path, monkeypatc
         np.testing.assert_array_equal(gt[k], ht[k], err_msg=f"triplet {k}")
 
 
+def test_builder_against_committed_golden():
+    """Disc sampler goldens (tests/golden/host_restatement_golden.npz): the stored priorities come from cv2, whose last bits
+    differ from the CUDA operator, so only the separation-4 list (no near-ties among its ~40 survivors) is compared exactly."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "host_restatement_golden.npz"))
+    poff, pc, _, _ = solver.build_constraints(g["sampler_color"][None], [(0, 0)], g["sampler_flow"][None], g["sampler_mask"][None], 4, 0.75)
+    np.testing.assert_array_equal(pc, g["sampler_sep4"])
+
+
 def test_builder_empty_and_bad_arguments():
     color = np.zeros((2, 8, 8, 3), np.float32)
     poff, pc, toff, tc = solver.build_constraints(color, np.zeros((0, 2), np.int32), None, None, 10, 1.0)

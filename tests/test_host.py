@@ -107,6 +107,46 @@ def test_video_dat_round_trip_and_processor_defaults(scene_dir, tmp_path):
     assert p.flowConsistancyThresh == np.float32(0.05)
 
 
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def test_raw_files_written_by_the_reference_python_writer(tmp_path):
+    """tests/golden/ref_writer_*.raw were written by the reference's own utils/image_io.py::save_raw_float32_image
+    (tests/golden/make_golden.py imports it unchanged): the C++ reader must decode them, and our writers must produce the
+    same bytes."""
+    arrs = np.load(os.path.join(GOLDEN, "ref_writer_arrays.npz"))
+    root = str(tmp_path / "v"); os.makedirs(root + "/d/depth"); os.makedirs(root + "/color_down")
+    open(root + "/frames.txt", "w").write("1\n7\n5\n0.0\n")
+    shutil.copy(os.path.join(GOLDEN, "ref_writer_disparity_5x7.raw"), root + "/d/depth/frame_000000.raw")
+    shutil.copy(os.path.join(GOLDEN, "ref_writer_color_5x7x3.raw"), root + "/color_down/frame_000000.raw")
+    v = lp.DepthVideo(); lp.DepthVideoImporter.importVideo(v, root, False)
+    v.createColorStream("down", "color_down", ".raw", CV_32FC3); v.createDepthStream("d", "d", [-1, -1])
+    src = np.asarray(v.depthStream(0).frame(0).sourceDepth())
+    disp = arrs["disp"]
+    with np.errstate(divide="ignore"):
+        want = np.where(np.isfinite(disp) & (disp > 0), np.float32(1.0) / disp, np.float32(0.0)).astype(np.float32)   # lib/DepthStream.cpp:200-211
+    np.testing.assert_array_equal(src, want)
+    np.testing.assert_array_equal(np.asarray(v.colorStream("down").frame(0).image()), arrs["color"])
+    # our Python and C++ writers emit the reference writer's bytes
+    synthetic_files.write_raw(str(tmp_path / "flow.raw"), arrs["flow"])
+    assert open(str(tmp_path / "flow.raw"), "rb").read() == open(os.path.join(GOLDEN, "ref_writer_flow_5x7x2.raw"), "rb").read()
+    np.testing.assert_array_equal(synthetic_files.read_raw(os.path.join(GOLDEN, "ref_writer_flow_5x7x2.raw")), arrs["flow"])
+
+
+def test_host_restatements_reproduce_their_goldens():
+    """oracle/host_ref.py (post-filter loop, disc sampler) against tests/golden/host_restatement_golden.npz."""
+    from tests.test_gpu_filter import make_filter_case
+    g = np.load(os.path.join(GOLDEN, "host_restatement_golden.npz"))
+    case, far_pairs, ff, fm = make_filter_case(F=5, w=20, h=12, seed=9, far=((2, 0), (2, 4)))
+    got = host_ref.flow_guided_filter(**case, first_out=1, num_out=3, frame_radius=2, spatial_radius=0, median=False)
+    np.testing.assert_array_equal(got, g["filter_mean_r0"])
+    got = host_ref.flow_guided_filter(**case, first_out=1, num_out=3, frame_radius=2, spatial_radius=1, median=True, far_pairs=far_pairs, far_flow=ff, far_mask=fm)
+    np.testing.assert_array_equal(got, g["filter_median_r1_far"])
+    for sep in (1, 4):
+        c, score = host_ref.pair_constraints(g["sampler_color"], g["sampler_flow"], g["sampler_mask"], sep, np.float32(0.75), score=g["sampler_score"])
+        np.testing.assert_array_equal(c, g[f"sampler_sep{sep}"])
+
+
 def test_constraints_match_numpy_cv2_restatement(scene_dir):
     import cv2
     sc, root, pairs, masks = scene_dir
