@@ -488,7 +488,7 @@ static int enqueue_factor_solve(rcvd_problem* p) {
       if (p->overlap) { CK(cudaEventRecord(p->ev_fork, st)); CK(cudaStreamWaitEvent(side, p->ev_fork, 0)); is = side; side_used = true; }
       k_trinv<<<dim3(npad / 16, lv.nframes), 256, (npad * 16 + 16 * (npad + 1)) * sizeof(double), is>>>(p->d_Lb, p->d_invT, p->d_invL, p->d_lvl_frames + lv.frame_off, npad);
       p->launches += 1; mark(P_TRINV);
-      if (lv.ntrsm > 0) { k_trsm_ll<<<dim3(tiles, lv.ntrsm), 128, trsm_ll_smem_bytes(npad), st>>>(p->d_T, p->d_Lb, p->d_invT, p->d_trsm_ll + lv.trsm_off, npad); p->launches++; mark(P_TRSM); }
+      if (lv.ntrsm > 0) { k_trsm_ll<<<dim3((npad + kTrsmStrip - 1) / kTrsmStrip, lv.ntrsm), 128, trsm_ll_smem_bytes(npad), st>>>(p->d_T, p->d_Lb, p->d_invT, p->d_trsm_ll + lv.trsm_off, npad); p->launches++; mark(P_TRSM); }
     } else {
       k_trinv<<<dim3(npad / 16, lv.nframes), 256, (npad * 16 + 16 * (npad + 1)) * sizeof(double), st>>>(p->d_Lb, p->d_invT, p->d_invL, p->d_lvl_frames + lv.frame_off, npad);
       p->launches += 1; mark(P_TRINV);

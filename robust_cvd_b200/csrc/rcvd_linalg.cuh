@@ -459,21 +459,26 @@ __global__ void __launch_bounds__(128, 4) k_gemm_nt(double* __restrict__ dst, co
 // k_trsm_ll: X_rk = A_rk * L_kk^{-T} by a left-looking tile recurrence on the fp64 tensor cores, needing only the 16x16
 // diagonal-tile inverses of k_potrf (no explicit inverse of L_kk):
 //     X[:, jt] = (A[:, jt] - sum_{pt<jt} X[:, pt] L[jt, pt]^T) * Di_jt^T          jt = 0 .. npad/16 - 1
-// One CTA = one 64-row strip of one block: 4 warps x 16 rows; the strip of X lives in shared memory
-// (64 x (npad+4) doubles), the L row panel of step jt is staged with cp.async one step ahead.
+// One CTA = one kTrsmStrip-row strip of one block: 4 warps x kTrsmRW rows; the strip of X lives in shared memory
+// (kTrsmStrip x (npad+4) doubles), the L row panel of step jt is staged with cp.async one step ahead.
 // ---------------------------------------------------------------------------
 struct TrsmTask { int dst; int src; int kframe; };   // T index, L block id, column frame
-__host__ __device__ inline size_t trsm_ll_smem_bytes(int npad) { return ((size_t)64 * (npad + 4) + 2 * 16 * (size_t)(npad + 4) + 2 * 16 * 20) * sizeof(double); }
+// strip = 4 warps x RW rows.  RW = 8 (32-row strips, 108 KB -> two CTAs per SM, twice the CTAs): every warp issues one DMMA per
+// 16 clk at best, so its 13-step chain costs (rows/8) x 728 DMMA x 16 clk -- halving the rows per warp halves the latency of a
+// launch that does not fill the machine (the dense tail), and two co-resident CTAs hide each other's staging waits elsewhere.
+constexpr int kTrsmRW = 8;
+constexpr int kTrsmStrip = 4 * kTrsmRW;
+__host__ __device__ inline size_t trsm_ll_smem_bytes(int npad) { return ((size_t)kTrsmStrip * (npad + 4) + 2 * 16 * (size_t)(npad + 4) + 2 * 16 * 20) * sizeof(double); }
 
 __global__ void __launch_bounds__(128) k_trsm_ll(double* __restrict__ T, const double* __restrict__ Lb, const double* __restrict__ invT,
                                                   const TrsmTask* __restrict__ tasks, int npad) {
   extern __shared__ __align__(16) double smx[];
   const int ld = npad + 4;                       // ld = 4 (mod 16): conflict-free DMMA fragment loads
-  double* Xs = smx;                              // [64][ld]
-  double* Ls = smx + (size_t)64 * ld;            // [2][16][ld]   L[jt*16 .. +15][0 .. jt*16)
+  double* Xs = smx;                              // [kTrsmStrip][ld]
+  double* Ls = smx + (size_t)kTrsmStrip * ld;            // [2][16][ld]   L[jt*16 .. +15][0 .. jt*16)
   double* Ds = Ls + (size_t)2 * 16 * ld;         // [2][16][20]   Di_jt
   const TrsmTask task = tasks[blockIdx.y];
-  const int m0 = blockIdx.x * 64;
+  const int m0 = blockIdx.x * kTrsmStrip;
   const size_t bs = (size_t)npad * npad;
   const double* A = Lb + (size_t)task.src * bs;
   const double* Lk = Lb + (size_t)task.kframe * bs;
@@ -481,9 +486,9 @@ __global__ void __launch_bounds__(128) k_trsm_ll(double* __restrict__ T, const d
   double* X = T + (size_t)task.dst * bs;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int nt = npad / 16;
-  const int rows = min(64, npad - m0);
+  const int rows = min(kTrsmStrip, npad - m0);
   // load the A strip (rows beyond the block are zero-filled)
-  for (int e = tid; e < 64 * (npad / 2); e += 128) {
+  for (int e = tid; e < kTrsmStrip * (npad / 2); e += 128) {
     const int r = e / (npad / 2), c = (e % (npad / 2)) * 2;
     const bool v = r < rows;
     cp_async16(&Xs[(size_t)r * ld + c], A + (size_t)(v ? m0 + r : 0) * npad + c, v);
@@ -496,44 +501,53 @@ __global__ void __launch_bounds__(128) k_trsm_ll(double* __restrict__ T, const d
     cp_async_commit();
   };
   stage(0);
-  const int wr = warp * 16;                       // this warp's rows inside the strip
+  constexpr int NI = kTrsmRW / 8;                 // m8 tiles per warp
+  const int wr = warp * kTrsmRW;                  // this warp's rows inside the strip
   for (int jt = 0; jt < nt; ++jt) {
     if (jt + 1 < nt) { stage(jt + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();
     const double* ls = Ls + (size_t)(jt & 1) * 16 * ld; const double* dsm = Ds + (jt & 1) * 320;
-    double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+    double acc[NI][2][2];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) { acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0; }
     for (int k4 = 0; k4 < jt * 4; ++k4) {
-      double af[2], bf[2];
+      double af[NI], bf[2];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) { af[i] = Xs[(size_t)(wr + i * 8 + g) * ld + k4 * 4 + t]; bf[i] = ls[(size_t)(i * 8 + g) * ld + k4 * 4 + t]; }
+      for (int i = 0; i < NI; ++i) af[i] = Xs[(size_t)(wr + i * 8 + g) * ld + k4 * 4 + t];
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
+      for (int j = 0; j < 2; ++j) bf[j] = ls[(size_t)(j * 8 + g) * ld + k4 * 4 + t];
+#pragma unroll
+      for (int i = 0; i < NI; ++i)
 #pragma unroll
         for (int j = 0; j < 2; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
     // Tt = A[:, jt] - acc, written back in place (each lane owns its C-fragment positions), then X[:, jt] = Tt * Di^T
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < NI; ++i)
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         double2* ptr = reinterpret_cast<double2*>(&Xs[(size_t)(wr + i * 8 + g) * ld + jt * 16 + j * 8 + 2 * t]);
         double2 v = *ptr; v.x -= acc[i][j][0]; v.y -= acc[i][j][1]; *ptr = v;
       }
     __syncwarp();
-    double out[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+    double out[NI][2][2];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) { out[i][0][0] = out[i][0][1] = out[i][1][0] = out[i][1][1] = 0.0; }
 #pragma unroll
     for (int k4 = 0; k4 < 4; ++k4) {
-      double af[2], bf[2];
+      double af[NI], bf[2];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) { af[i] = Xs[(size_t)(wr + i * 8 + g) * ld + jt * 16 + k4 * 4 + t]; bf[i] = dsm[(i * 8 + g) * 20 + k4 * 4 + t]; }
+      for (int i = 0; i < NI; ++i) af[i] = Xs[(size_t)(wr + i * 8 + g) * ld + jt * 16 + k4 * 4 + t];
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
+      for (int j = 0; j < 2; ++j) bf[j] = dsm[(j * 8 + g) * 20 + k4 * 4 + t];
+#pragma unroll
+      for (int i = 0; i < NI; ++i)
 #pragma unroll
         for (int j = 0; j < 2; ++j) dmma_8x8x4(out[i][j][0], out[i][j][1], af[i], bf[j]);
     }
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < NI; ++i)
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int r = wr + i * 8 + g, cidx = jt * 16 + j * 8 + 2 * t;
