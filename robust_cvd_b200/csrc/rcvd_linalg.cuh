@@ -369,10 +369,10 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
 
 // One 16-deep K stage of a warp's (NI*8) x (NJ*8) sub-tile: NI/NJ are compile-time so that no tensor instruction is predicated
 // (a predicated mma.sync costs a WARPSYNC + branch pair each).
-template <int NI, int NJ>
+template <int NI, int NJ, int K4 = 4>
 __device__ __forceinline__ void gemm_stage(const double* __restrict__ as, const double* __restrict__ bsm, double (&acc)[4][4][2], int wm, int wn, int g, int t) {
 #pragma unroll
-  for (int k4 = 0; k4 < 4; ++k4) {
+  for (int k4 = 0; k4 < K4; ++k4) {
     double af[NI > 0 ? NI : 1], bf[NJ > 0 ? NJ : 1];
 #pragma unroll
     for (int i = 0; i < NI; ++i) af[i] = as[(wm + i * 8 + g) * kGemmLd + k4 * 4 + t];
@@ -387,7 +387,9 @@ __device__ __forceinline__ void gemm_stage(const double* __restrict__ as, const 
 
 __global__ void __launch_bounds__(128, 4) k_gemm_nt(double* __restrict__ dst, const double* __restrict__ Abase, const double* __restrict__ Bbase,
                                                   const GemmTask* __restrict__ tasks, const int2* __restrict__ pairs,
-                                                  int npad, double alpha, double beta) {
+                                                  int npad, int neff, double alpha, double beta) {
+  // neff = per-frame unknowns rounded up to 8 (<= npad): rows / columns / K beyond it are exact zeros in every operand
+  // (padding of the factor blocks), so their mma tiles and the tail K steps are never issued (199 -> 200 of 208: -11 % DMMA)
   __shared__ __align__(16) double As[2][64 * kGemmLd];
   __shared__ __align__(16) double Bs[2][64 * kGemmLd];
   const GemmTask task = tasks[blockIdx.z];
@@ -401,7 +403,9 @@ __global__ void __launch_bounds__(128, 4) k_gemm_nt(double* __restrict__ dst, co
   const int kchunks = (task.lower_only & 2) ? min(npad, n0 + 64) / 16 : npad / 16;
   const int total = task.count * kchunks;
   // 8-row / 8-column mma tiles of this warp that lie inside the matrix (npad is a multiple of 16, tiles are 64)
-  const int ni = min(4, max(0, (npad - (m0 + wm)) / 8)), nj = min(4, max(0, (npad - (n0 + wn)) / 8));
+  const int ni = min(4, max(0, (neff - (m0 + wm)) / 8)), nj = min(4, max(0, (neff - (n0 + wn)) / 8));
+  const int lastk = (task.lower_only & 2) ? -1 : kchunks - 1;          // K chunk that holds the tail of neff
+  const int tailk4 = (neff - 16 * (npad / 16 - 1) + 3) / 4;            // 1..4 valid 4-deep K steps in that chunk
   double acc[4][4][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -431,21 +435,28 @@ __global__ void __launch_bounds__(128, 4) k_gemm_nt(double* __restrict__ dst, co
     __syncthreads();
     const double* as = As[st]; const double* bsm = Bs[st];
     // warp-uniform dispatch on the number of in-range 8-wide mma tiles (npad is a multiple of 16 -> ni, nj in {0, 2, 4})
-    if (ni == 4 && nj == 4) gemm_stage<4, 4>(as, bsm, acc, wm, wn, g, t);
-    else if (ni == 4 && nj == 2) gemm_stage<4, 2>(as, bsm, acc, wm, wn, g, t);
-    else if (ni == 2 && nj == 4) gemm_stage<2, 4>(as, bsm, acc, wm, wn, g, t);
-    else if (ni == 2 && nj == 2) gemm_stage<2, 2>(as, bsm, acc, wm, wn, g, t);
+    const bool tail = (kk % kchunks) == lastk && tailk4 == 2;       // neff = 8 (mod 16): only two K steps of the last chunk are non-zero
+#define RCVD_GS(NI_, NJ_) case NI_ * 8 + NJ_: if (tail) gemm_stage<NI_, NJ_, 2>(as, bsm, acc, wm, wn, g, t); else gemm_stage<NI_, NJ_, 4>(as, bsm, acc, wm, wn, g, t); break;
+    if (ni == 4 && nj == 4 && !tail) gemm_stage<4, 4, 4>(as, bsm, acc, wm, wn, g, t);   // interior tiles: the hot path, tested first
+    else switch (ni * 8 + nj) {
+      RCVD_GS(4, 4) RCVD_GS(4, 3) RCVD_GS(4, 2) RCVD_GS(4, 1)
+      RCVD_GS(3, 4) RCVD_GS(3, 3) RCVD_GS(3, 2) RCVD_GS(3, 1)
+      RCVD_GS(2, 4) RCVD_GS(2, 3) RCVD_GS(2, 2) RCVD_GS(2, 1)
+      RCVD_GS(1, 4) RCVD_GS(1, 3) RCVD_GS(1, 2) RCVD_GS(1, 1)
+      default: break;
+    }
+#undef RCVD_GS
     __syncthreads();
   }
   double* C = dst + (size_t)task.dst * bs;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int row = m0 + wm + i * 8 + g;
-    if (row >= npad) continue;
+    if (row >= neff) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int col = n0 + wn + j * 8 + 2 * t;
-      if (col >= npad) continue;
+      if (col >= neff) continue;
       double2* ptr = reinterpret_cast<double2*>(C + (size_t)row * npad + col);
       double2 o;
       if (beta != 0.0) { o = *ptr; o.x = beta * o.x + alpha * acc[i][j][0]; o.y = beta * o.y + alpha * acc[i][j][1]; }

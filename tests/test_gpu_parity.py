@@ -50,6 +50,11 @@ def test_linear_solve(name, overrides):
     res = np.linalg.norm(A @ y - b) / np.linalg.norm(b)
     assert res < 1e-8, res
     assert np.linalg.norm(y - y_ref) / np.linalg.norm(y_ref) < 1e-6
+    # solver variants must agree to round-off: untrimmed update GEMMs, single-stream graph, explicit-inverse TRSM
+    for setter in (lambda: G.set_trim_gemm(False), lambda: G.set_overlap(False), lambda: G.set_trsm_ll(False)):
+        setter()
+        y2 = G.debug_linear_solve(S, D2, b)
+        assert np.linalg.norm(y2 - y) / np.linalg.norm(y) < 1e-9
 
 
 @pytest.mark.parametrize("name,overrides", helpers.VARIANTS, ids=[v[0] for v in helpers.VARIANTS])
