@@ -210,7 +210,7 @@ struct rcvd_problem {
   // multi GPU
   int nranks = 1, rank = 0; nccl::Comm comm = nullptr;
   int64_t launches = 0, graph_launches = 0;
-  std::vector<double> h_state; bool state_dirty = false; bool use_fast = true; bool overlap = true; bool trim_gemm = true; int side_slice = 0; bool allow_trsm_ll = true; bool sub_solves = false; int order_slack = 3;   // multiple elimination with degree slack 3 (measured best at config 2); -1: greedy minimum degree
+  std::vector<double> h_state; bool state_dirty = false; bool use_fast = true; bool overlap = true; bool trim_gemm = true; bool potrf_chain_warp = true; int side_slice = 0; bool allow_trsm_ll = true; bool sub_solves = false; int order_slack = 3;   // multiple elimination with degree slack 3 (measured best at config 2); -1: greedy minimum degree
   cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   double *d_g2 = nullptr, *d_delta = nullptr; int* h_fail = nullptr;
   cudaEvent_t ev[8] = {nullptr};
@@ -480,7 +480,7 @@ static int enqueue_factor_solve(rcvd_problem* p) {
   for (size_t li = 0; li < p->levels.size(); ++li) {
     const Level& lv = p->levels[li];
     if (potrf_smem_bytes(npad) <= 220 * 1024)
-      k_potrf_smem<<<lv.nframes, kPotrfSmemThreads, potrf_smem_bytes(npad), st>>>(p->d_Lb, p->d_invT, p->d_lvl_frames + lv.frame_off, npad, p->d_fail);
+      k_potrf_smem<<<lv.nframes, kPotrfSmemThreads, potrf_smem_bytes(npad), st>>>(p->d_Lb, p->d_invT, p->d_lvl_frames + lv.frame_off, npad, p->d_fail, p->potrf_chain_warp ? 1 : 0);
     else
       k_potrf<<<lv.nframes, kPotrfThreads, npad * 17 * sizeof(double), st>>>(p->d_Lb, p->d_invT, p->d_lvl_frames + lv.frame_off, npad, p->d_fail);
     p->launches += 1; mark(P_POTRF);
@@ -1185,6 +1185,8 @@ RCVD_API int32_t rcvd_debug_set_trsm_ll(rcvd_problem* p, int32_t on) { if (!p) r
 RCVD_API int32_t rcvd_debug_set_side_slice(rcvd_problem* p, int32_t ctas) { if (!p) return RCVD_ERR_INVALID; p->side_slice = ctas; if (p->solve_graph) { cudaGraphExecDestroy(p->solve_graph); p->solve_graph = nullptr; } return RCVD_OK; }
 // Test / bench hook: 0 = update GEMMs over the padded size, 1 (default) = trimmed to the unknowns rounded to 8.
 RCVD_API int32_t rcvd_debug_set_trim_gemm(rcvd_problem* p, int32_t on) { if (!p) return RCVD_ERR_INVALID; p->trim_gemm = on != 0; if (p->solve_graph) { cudaGraphExecDestroy(p->solve_graph); p->solve_graph = nullptr; } return RCVD_OK; }
+// Test / bench hook: 1 (default) = warp 0 of k_potrf_smem only runs the pivot-tile chain, 0 = it also takes trailing tiles.
+RCVD_API int32_t rcvd_debug_set_potrf_chain_warp(rcvd_problem* p, int32_t on) { if (!p) return RCVD_ERR_INVALID; p->potrf_chain_warp = on != 0; if (p->solve_graph) { cudaGraphExecDestroy(p->solve_graph); p->solve_graph = nullptr; } return RCVD_OK; }
 RCVD_API int32_t rcvd_debug_set_fast_path(rcvd_problem* p, int32_t on) { if (!p) return RCVD_ERR_INVALID; p->use_fast = on != 0; return RCVD_OK; }
 RCVD_API int32_t rcvd_solve(rcvd_problem* p, const rcvd_solve_options* opt, rcvd_solve_summary* summary) {
   if (!p || !summary) return set_err(RCVD_ERR_INVALID, "null argument");

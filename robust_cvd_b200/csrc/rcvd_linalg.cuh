@@ -158,6 +158,9 @@ __device__ __forceinline__ void tile_mma_nt(const double* __restrict__ At, const
 
 // Register-resident right-looking Cholesky of one 16x16 tile by a single warp (lane i mod 16 owns row i).
 // Writes L back to the swizzled tile and the reciprocal pivots 1/l_jj to pinv[0..15].
+// (Measured dead ends, tools/potrf_phases.cu: a branch-free variant with an fp32-seeded Newton rsqrt: 7.5 k cycles per tile
+// against 5.6 k -- the F2F conversions cost more than the library's MUFU.RSQ64H path; a rotated-row loop form that is not
+// unrolled over j: 17 k cycles.)
 __device__ __forceinline__ void warp_chol16(double* __restrict__ D, double* __restrict__ pinv, int lane, int* __restrict__ fail) {
   const int i = lane & 15;
   double a[16];
@@ -193,7 +196,7 @@ __device__ long long g_potrf_phase[8];
 #endif
 
 __global__ void __launch_bounds__(kPotrfSmemThreads) k_potrf_smem(double* __restrict__ Lb, double* __restrict__ invT,
-                                                                   const int* __restrict__ frames, int npad, int* __restrict__ fail) {
+                                                                   const int* __restrict__ frames, int npad, int* __restrict__ fail, int chain_warp) {
   extern __shared__ __align__(16) double tiles[];
   const int frame = frames[blockIdx.x];
   double* A = Lb + (size_t)frame * npad * npad;
@@ -260,8 +263,10 @@ __global__ void __launch_bounds__(kPotrfSmemThreads) k_potrf_smem(double* __rest
     POTRF_PHASE(3);
     // ---- trailing update (DMMA) with lookahead: warp 0 updates tile (jb+1, jb+1) first and factors it at once ----
     const int m = nt - jb - 1, ntr = m * (m + 1) / 2;
-    for (int tl = warp; tl < ntr; tl += nw) {
-      // tile order: tl = 0 is (jb+1, jb+1) and goes to warp 0
+    // warp 0 owns the chain: it updates tile (jb+1, jb+1) and factors it at once (lookahead); the other warps share the rest
+    // (measured: 88.7 -> 83.0 us per 208x208 block in tools/potrf_phases.cu)
+    for (int tl = (chain_warp ? (warp == 0 ? 0 : warp) : warp); tl < ((chain_warp && warp == 0) ? min(ntr, 1) : ntr); tl += (chain_warp ? nw - 1 : nw)) {
+      // tile order: tl = 0 is (jb+1, jb+1)
       int ti = (int)((sqrtf(8.f * tl + 1.f) - 1.f) * 0.5f);
       while ((ti + 1) * (ti + 2) / 2 <= tl) ++ti;
       while (ti * (ti + 1) / 2 > tl) --ti;

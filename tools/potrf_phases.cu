@@ -16,7 +16,7 @@ int main() {
   for (int rep = 0; rep < 3; ++rep) {
     cudaMemcpy(dA, A.data(), A.size() * 8, cudaMemcpyHostToDevice);
     long long z[8] = {0}; cudaMemcpyToSymbol(g_potrf_phase, z, sizeof(z));
-    cudaEventRecord(e0); k_potrf_smem<<<1, kPotrfSmemThreads, potrf_smem_bytes(n)>>>(dA, dT, dF, n, dfail); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    cudaEventRecord(e0); k_potrf_smem<<<1, kPotrfSmemThreads, potrf_smem_bytes(n)>>>(dA, dT, dF, n, dfail, 1); cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     long long ph[8]; cudaMemcpyFromSymbol(ph, g_potrf_phase, sizeof(ph));
     printf("rep %d: %.1f us; cycles: load %lld, first chol %lld, panel(thread0) %lld, wait-panel %lld, update-to-lookahead %lld, lookahead chol %lld, rest of update %lld, wait-update %lld  (%s)\n",
