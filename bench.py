@@ -39,7 +39,7 @@ WORKLOADS = {
 METRIC = "flow_residual_constraints_per_sec_per_gn_iteration"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/), config 2;
 # per-launch averages of the captured launches.
-NCU_TRAFFIC = {"gemm_nt": 18.05e6, "accumulate": 149.1e6}   # gemm_nt: mean of the 3 captured launches (grids 288/1136/320 CTAs), profiles/r1_ncu_k_gemm_nt.txt
+NCU_TRAFFIC = {"gemm_nt": 18.49e6, "accumulate": 149.1e6}   # gemm_nt: mean of the 3 captured launches (grids 288/1200/352 CTAs), profiles/r1_ncu_k_gemm_nt.txt
 
 
 def build_case(wl, frames=None, sep=None, seed=2, valid_fraction=1.0):
