@@ -263,3 +263,75 @@ def test_filter_depth_sequence_through_lib_python(tmp_path):
         assert list(a.depthXform().params()) == list(b.depthXform().params())
         assert a.intrinsics.vFov == b.intrinsics.vFov
     np.testing.assert_allclose(np.array(v2.depthStream(1).frame(3).depth()), got[2], rtol=2e-6)   # disparity round trip
+
+
+def test_filter_far_connections_median_and_partial_range(tmp_path):
+    """Op.FlowGuidedFilter with farConnections + median + spatialRadius 1 on the frame range 2-4 of a 7-frame video:
+    the host side keeps every frame on the device (far targets may lie anywhere) and windows reach back before the range."""
+    import cv2
+    import lib_python as lp
+    from oracle import host_ref
+    from scipy.spatial.transform import Rotation
+    root = str(tmp_path / "scene")
+    N, W, H = 7, 40, 28
+    sc = synthetic.Scene(N, W, H, seed=11, motion=0.05, rot_deg=0.5)
+    synthetic_files.write_scene(sc, root)       # hierarchical2 pairs: consecutive frames both ways + (0,2),(2,0),(0,4),(4,0),(2,4),(4,2),(4,6),(6,4)
+    v = lp.DepthVideo(); lp.DepthVideoImporter.importVideo(v, root, False)
+    v.createColorStream("down", "color_down", ".raw", CV_32FC3)
+    v.createDepthStream("depth_midas2", "depth_midas2", [-1, -1])
+    src = v.depthStream(0)
+    for f in range(N):
+        df = src.frame(f); e = df.extrinsics; e.position = np.asarray(sc.t[f], np.float32)
+        e.orientation = lp._makeQuat(*[float(c) for c in Rotation.from_matrix(sc.R[f]).as_quat().astype(np.float32)]); df.extrinsics = e
+    v.createDepthStream("filtered", "depth_filtered", [src.width(), src.height()])
+    proc = lp.DepthVideoProcessor(v)
+    params = lp.DepthVideoProcessor.Params(); params.frameRange.fromString("2-4")
+    params.op = lp.DepthVideoProcessor.Op.Copy; params.sourceDepthStream = 0; params.depthStream = 1; proc.process(params)
+    params.op = lp.DepthVideoProcessor.Op.FlowGuidedFilter; params.frameRadius = 1; params.spatialRadius = 1; params.median = True; params.farConnections = True
+    proc.process(params)
+    got = np.stack([np.array(v.depthStream(1).frame(f).depth()) for f in (2, 3, 4)])
+    depth = np.stack([np.array(src.frame(f).depth()) for f in range(N)])
+    cams = np.zeros((N, 9), np.float32)
+    for f in range(N):
+        df = src.frame(f); e = df.extrinsics
+        cams[f, :3] = e.position; cams[f, 3:7] = [e.orientation.x(), e.orientation.y(), e.orientation.z(), e.orientation.w()]; cams[f, 7] = df.intrinsics.hFov; cams[f, 8] = df.intrinsics.vFov
+
+    def fm(a, b):
+        return (synthetic_files.read_raw(os.path.join(root, "flow", f"flow_{a:06d}_{b:06d}.raw")), cv2.imread(os.path.join(root, "flow_mask", f"mask_{a:06d}_{b:06d}.png"), cv2.IMREAD_GRAYSCALE))
+    fwd = np.zeros((N, H, W, 2), np.float32); fwm = np.zeros((N, H, W), np.uint8); bwd = np.zeros_like(fwd); bwm = np.zeros_like(fwm)
+    for f in range(N - 1):
+        fwd[f], fwm[f] = fm(f, f + 1); bwd[f + 1], bwm[f + 1] = fm(f + 1, f)
+    # far connections of frames 2..4 (frameRadius 1, range last = 4): flow files (frame, fi) with fi outside [max(0, frame-1), min(4, frame+1)], sorted
+    far = []
+    for name in sorted(os.listdir(os.path.join(root, "flow"))):
+        a, b = int(name[5:11]), int(name[12:18])
+        if 2 <= a <= 4 and (b < max(0, a - 1) or b > min(4, a + 1)):
+            far.append((a, b))
+    assert (2, 0) in far and (4, 6) in far and (4, 5) in far          # a target beyond the range end counts as "far" (f1 is clamped to the range)
+    ff = np.stack([fm(a, b)[0] for a, b in far]); fmk = np.stack([fm(a, b)[1] for a, b in far])
+    want = host_ref.flow_guided_filter(depth, cams, fwd, fwm, bwd, bwm, first_out=2, num_out=3, frame_radius=1, spatial_radius=1, median=True,
+                                       inv_aspect=v.invAspect(), far_pairs=far, far_flow=ff, far_mask=fmk)
+    assert np.isclose(got, want, rtol=1e-5).mean() >= 0.995, np.abs(got - want).max()
+    np.testing.assert_array_equal(np.array(v.depthStream(1).frame(1).depth() is None), True)     # frames outside the range were not created
+
+
+def test_constraint_builder_on_a_frame_sub_range(tmp_path, monkeypatch):
+    """FlowConstraintsParams.frameRange = 2-5 of 8 frames: local frame indices of the GPU builder have an offset; same lists as the host builder."""
+    import lib_python as lp
+    root = str(tmp_path / "scene")
+    sc = synthetic.Scene(8, 64, 48, seed=13)
+    synthetic_files.write_scene(sc, root)
+
+    def run(which):
+        monkeypatch.setenv("RCVD_CONSTRAINT_BUILDER", which)
+        v = lp.DepthVideo(); lp.DepthVideoImporter.importVideo(v, root, False)
+        v.createColorStream("down", "color_down", ".raw", CV_32FC3); v.createDepthStream("depth_midas2", "depth_midas2", [-1, -1])
+        fp = lp.FlowConstraintsParams(); fp.frameRange.fromString("2-5"); fp.frameRange.resolve(v.numFrames(), True); fp.doNotUseCache = True
+        fc = lp.FlowConstraintsCollection(v, fp)
+        return {k: np.asarray(a[0]) for k, a in fc._pairs().items()}, {k: np.asarray(a[0]) for k, a in fc._triplets().items()}
+    gp, gt = run("gpu"); hp, ht = run("host")
+    assert sorted(gp) == sorted(hp) and all(2 <= a <= 5 and 2 <= b <= 5 for a, b in gp) and len(gp) >= 6 and sorted(gt) == [3, 4]
+    for k in gp:
+        np.testing.assert_array_equal(gp[k], hp[k])
+    for k in gt:
+        np.testing.assert_array_equal(gt[k], ht[k])
