@@ -442,9 +442,7 @@ static int build_structure(rcvd_problem* p) {
   k_finalize_mask<<<(int)((Upad + 255) / 256), 256, 0, p->stream>>>(p->cfg, L, p->d_active, N);
   CK(cudaGetLastError());
   // kernels that need > 48 KB dynamic smem
-  const int dyn = npad * 17 * (int)sizeof(double);
-  if (dyn > 200 * 1024) return set_err(RCVD_ERR_INVALID, "frame block too large for the single-CTA factor kernel (npad=%d)", npad);
-  CK(cudaFuncSetAttribute(k_potrf, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+  if ((npad * 16 + 16 * (npad + 1)) * (int)sizeof(double) > 220 * 1024) return set_err(RCVD_ERR_INVALID, "frame block too large for the panel-inverse kernel (npad=%d)", npad);
   CK(cudaFuncSetAttribute(k_trinv, cudaFuncAttributeMaxDynamicSharedMemorySize, (npad * 16 + 16 * (npad + 1)) * (int)sizeof(double)));
   CK(cudaFuncSetAttribute(k_accumulate_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem));
   p->use_trsm_ll = p->allow_trsm_ll && trsm_ll_smem_bytes(npad) <= 220 * 1024;
@@ -481,8 +479,17 @@ static int enqueue_factor_solve(rcvd_problem* p) {
     const Level& lv = p->levels[li];
     if (potrf_smem_bytes(npad) <= 220 * 1024)
       k_potrf_smem<<<lv.nframes, kPotrfSmemThreads, potrf_smem_bytes(npad), st>>>(p->d_Lb, p->d_invT, p->d_lvl_frames + lv.frame_off, npad, p->d_fail, p->potrf_chain_warp ? 1 : 0);
-    else
-      k_potrf<<<lv.nframes, kPotrfThreads, npad * 17 * sizeof(double), st>>>(p->d_Lb, p->d_invT, p->d_lvl_frames + lv.frame_off, npad, p->d_fail);
+    else {
+      // large blocks: 16-wide panels, panel factor on one CTA per frame, trailing update on the whole machine
+      const int nt16 = npad / 16;
+      for (int jb = 0; jb < nt16; ++jb) {
+        k_potrf_panel<<<lv.nframes, kPotrfThreads, 0, st>>>(p->d_Lb, p->d_invT, p->d_lvl_frames + lv.frame_off, npad, jb, p->d_fail);
+        p->launches += 1;
+        const int m = npad - (jb + 1) * 16;
+        if (m > 0) { const int n64 = (m + 63) / 64; k_potrf_trail<<<dim3(n64 * (n64 + 1) / 2, lv.nframes), 128, 0, st>>>(p->d_Lb, p->d_lvl_frames + lv.frame_off, npad, jb); p->launches += 1; }
+      }
+      p->launches -= 1;   // (the common increment below)
+    }
     p->launches += 1; mark(P_POTRF);
     if (p->use_trsm_ll) {
       // the explicit inverse is only needed by the (much later) substitution phase: compute it off the critical path

@@ -15,111 +15,83 @@
 namespace rcvd {
 
 // ---------------------------------------------------------------------------
-// k_potrf: in-place lower Cholesky of diagonal blocks; right-looking, 16-wide panels.
+// Large diagonal blocks (npad > 224: the lower triangle no longer fits in one CTA's shared memory), right-looking with
+// 16-wide panels, TWO launches per panel so that the O(n^3) trailing update runs on the whole machine:
+//   k_potrf_panel (one CTA per frame)            pivot-tile Cholesky + tile inverse (-> invT) + panel X = A Di^T
+//   k_potrf_trail (64x64 tiles x frames, DMMA)   A[i][j] -= X_i X_j^T on the trailing lower triangle
+// (a single-CTA version of this loop spent 6.5 ms per level at npad = 784; `bench.py --workload config4... --frames 160`).
 // ---------------------------------------------------------------------------
 constexpr int kPotrfThreads = 256;
 
-__global__ void __launch_bounds__(kPotrfThreads) k_potrf(double* __restrict__ Lb, double* __restrict__ invT,
-                                                          const int* __restrict__ frames, int npad, int* __restrict__ fail) {
-  extern __shared__ double panel[];           // [npad][17] (padded rows: conflict-free column walks)
+__global__ void __launch_bounds__(kPotrfThreads) k_potrf_panel(double* __restrict__ Lb, double* __restrict__ invT,
+                                                                const int* __restrict__ frames, int npad, int jb, int* __restrict__ fail) {
   __shared__ double D[16][17];
   __shared__ double Di[16][17];
   const int frame = frames[blockIdx.x];
   double* A = Lb + (size_t)frame * npad * npad;
   double* iT = invT + (size_t)frame * npad * 16;   // nt tiles of 16x16
-  const int nt = npad / 16;
   const int tid = threadIdx.x;
-  for (int jb = 0; jb < nt; ++jb) {
-    const int j0 = jb * 16;
-    {
-      const int r = tid >> 4, cc = tid & 15;
-      D[r][cc] = (cc <= r) ? A[(size_t)(j0 + r) * npad + j0 + cc] : 0.0;
-    }
-    __syncthreads();
-    if (tid < 32) {
-      // unblocked Cholesky of the 16x16 tile, lane i owns row i
-      const int i = tid;
-      for (int j = 0; j < 16; ++j) {
-        if (i == j) {
-          double d = D[j][j];
-          for (int q = 0; q < j; ++q) d -= D[j][q] * D[j][q];
-          if (!(d > 0.0) || !isfinite(d)) { *fail = 1; d = 1.0; }
-          D[j][j] = sqrt(d);
-        }
-        __syncwarp();
-        if (i > j && i < 16) {
-          double s = D[i][j];
-          for (int q = 0; q < j; ++q) s -= D[i][q] * D[j][q];
-          D[i][j] = s / D[j][j];
-        }
-        __syncwarp();
+  const int j0 = jb * 16;
+  {
+    const int r = tid >> 4, cc = tid & 15;
+    D[r][cc] = (cc <= r) ? A[(size_t)(j0 + r) * npad + j0 + cc] : 0.0;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    // unblocked Cholesky of the 16x16 tile, lane i owns row i
+    const int i = tid;
+    for (int j = 0; j < 16; ++j) {
+      if (i == j) {
+        double d = D[j][j];
+        for (int q = 0; q < j; ++q) d -= D[j][q] * D[j][q];
+        if (!(d > 0.0) || !isfinite(d)) { *fail = 1; d = 1.0; }
+        D[j][j] = sqrt(d);
       }
-      // inverse of the lower-triangular tile: lane c computes column c
-      if (i < 16) {
-        const int cidx = i;
-        double xcol[16];
-#pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          double s = (r == cidx) ? 1.0 : 0.0;
-#pragma unroll
-          for (int q = 0; q < 16; ++q) if (q < r) s -= D[r][q] * xcol[q];
-          xcol[r] = (r < cidx) ? 0.0 : s / D[r][r];
-        }
-#pragma unroll
-        for (int r = 0; r < 16; ++r) Di[r][cidx] = xcol[r];
+      __syncwarp();
+      if (i > j && i < 16) {
+        double s = D[i][j];
+        for (int q = 0; q < j; ++q) s -= D[i][q] * D[j][q];
+        D[i][j] = s / D[j][j];
       }
+      __syncwarp();
     }
-    __syncthreads();
-    {
-      const int r = tid >> 4, cc = tid & 15;
-      A[(size_t)(j0 + r) * npad + j0 + cc] = D[r][cc];
-      iT[(size_t)jb * 256 + r * 16 + cc] = Di[r][cc];
-    }
-    // panel solve: X[i][:] = A[i][j0..j0+15] * Di^T for rows below the tile
-    const int below = npad - (j0 + 16);
-    for (int rr = tid; rr < below; rr += kPotrfThreads) {
-      const int i = j0 + 16 + rr;
-      double a[16], xo[16];
-      double* row = A + (size_t)i * npad + j0;
+    // inverse of the lower-triangular tile: lane c computes column c
+    if (i < 16) {
+      const int cidx = i;
+      double xcol[16];
 #pragma unroll
-      for (int q = 0; q < 16; ++q) a[q] = row[q];
+      for (int r = 0; r < 16; ++r) {
+        double s = (r == cidx) ? 1.0 : 0.0;
 #pragma unroll
-      for (int cc = 0; cc < 16; ++cc) {
-        double s = 0.0;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) if (q <= cc) s += a[q] * Di[cc][q];
-        xo[cc] = s;
+        for (int q = 0; q < 16; ++q) if (q < r) s -= D[r][q] * xcol[q];
+        xcol[r] = (r < cidx) ? 0.0 : s / D[r][r];
       }
 #pragma unroll
-      for (int q = 0; q < 16; ++q) { row[q] = xo[q]; panel[(size_t)rr * 17 + q] = xo[q]; }
+      for (int r = 0; r < 16; ++r) Di[r][cidx] = xcol[r];
     }
-    __syncthreads();
-    // trailing update of the lower tiles: A[ti][tj] -= P[ti] P[tj]^T, jb < tj <= ti
-    const int m = nt - jb - 1;
-    const int ntiles = m * (m + 1) / 2;
-    const int warp = tid >> 5, lane = tid & 31, nw = kPotrfThreads / 32;
-    for (int tl = warp; tl < ntiles; tl += nw) {
-      // unrank (ti >= tj) from tl
-      int ti = (int)((sqrt(8.0 * tl + 1.0) - 1.0) * 0.5);
-      while ((ti + 1) * (ti + 2) / 2 <= tl) ++ti;
-      while (ti * (ti + 1) / 2 > tl) --ti;
-      const int tj = tl - ti * (ti + 1) / 2;
-      const int r = lane >> 1, c0 = (lane & 1) * 8;
-      const double* pa = panel + (size_t)(ti * 16 + r) * 17;
-      double acc[8];
+  }
+  __syncthreads();
+  {
+    const int r = tid >> 4, cc = tid & 15;
+    A[(size_t)(j0 + r) * npad + j0 + cc] = D[r][cc];
+    iT[(size_t)jb * 256 + r * 16 + cc] = Di[r][cc];
+  }
+  // panel solve: X[i][:] = A[i][j0..j0+15] * Di^T for rows below the tile
+  const int below = npad - (j0 + 16);
+  for (int rr = tid; rr < below; rr += kPotrfThreads) {
+    double a[16], xo[16];
+    double* row = A + (size_t)(j0 + 16 + rr) * npad + j0;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+    for (int q = 0; q < 16; ++q) a[q] = row[q];
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const double av = pa[q];
+    for (int cc = 0; cc < 16; ++cc) {
+      double s = 0.0;
 #pragma unroll
-        for (int cc = 0; cc < 8; ++cc) acc[cc] += av * panel[(size_t)(tj * 16 + c0 + cc) * 17 + q];
-      }
-      double* out = A + (size_t)(j0 + 16 + ti * 16 + r) * npad + j0 + 16 + tj * 16 + c0;
-#pragma unroll
-      for (int cc = 0; cc < 8; ++cc) out[cc] -= acc[cc];
+      for (int q = 0; q < 16; ++q) if (q <= cc) s += a[q] * Di[cc][q];
+      xo[cc] = s;
     }
-    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 16; ++q) row[q] = xo[q];
   }
 }
 
@@ -467,6 +439,53 @@ __global__ void __launch_bounds__(128, 4) k_gemm_nt(double* __restrict__ dst, co
       if (beta != 0.0) { o = *ptr; o.x = beta * o.x + alpha * acc[i][j][0]; o.y = beta * o.y + alpha * acc[i][j][1]; }
       else { o.x = alpha * acc[i][j][0]; o.y = alpha * acc[i][j][1]; }
       *ptr = o;
+    }
+  }
+}
+
+// k_potrf_trail: rank-16 trailing update of the large-block Cholesky (see k_potrf_panel).  grid = (lower 64x64 tile pairs of
+// the trailing matrix, frames); 4 warps of 32x32, one 16-deep DMMA stage; entries above the diagonal are not touched.
+__global__ void __launch_bounds__(128, 4) k_potrf_trail(double* __restrict__ Lb, const int* __restrict__ frames, int npad, int jb) {
+  __shared__ __align__(16) double Ps[2][64 * kGemmLd];
+  const int frame = frames[blockIdx.y];
+  double* A = Lb + (size_t)frame * npad * npad;
+  const int j0 = jb * 16, j1 = j0 + 16;
+  int ti = (int)((sqrtf(8.f * blockIdx.x + 1.f) - 1.f) * 0.5f);
+  while ((ti + 1) * (ti + 2) / 2 <= (int)blockIdx.x) ++ti;
+  while (ti * (ti + 1) / 2 > (int)blockIdx.x) --ti;
+  const int tj = blockIdx.x - ti * (ti + 1) / 2;
+  const int m0 = j1 + ti * 64, n0 = j1 + tj * 64;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  for (int e = tid; e < 64 * 8; e += 128) {     // 64 rows x 8 double2
+    const int row = e >> 3, kc = (e & 7) * 2;
+    const bool va = (m0 + row) < npad, vb = (n0 + row) < npad;
+    cp_async16(&Ps[0][row * kGemmLd + kc], A + (size_t)(va ? m0 + row : 0) * npad + j0 + kc, va);
+    cp_async16(&Ps[1][row * kGemmLd + kc], A + (size_t)(vb ? n0 + row : 0) * npad + j0 + kc, vb);
+  }
+  cp_async_commit(); cp_async_wait<0>();
+  __syncthreads();
+  const int ni = min(4, max(0, (npad - (m0 + wm)) / 8)), nj = min(4, max(0, (npad - (n0 + wn)) / 8));
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+  if (ni == 4 && nj == 4) gemm_stage<4, 4>(Ps[0], Ps[1], acc, wm, wn, g, t);
+  else if (ni == 4 && nj == 2) gemm_stage<4, 2>(Ps[0], Ps[1], acc, wm, wn, g, t);
+  else if (ni == 2 && nj == 4) gemm_stage<2, 4>(Ps[0], Ps[1], acc, wm, wn, g, t);
+  else if (ni == 2 && nj == 2) gemm_stage<2, 2>(Ps[0], Ps[1], acc, wm, wn, g, t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = m0 + wm + i * 8 + g;
+    if (i >= ni) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = n0 + wn + j * 8 + 2 * t;
+      if (j >= nj || col > row) continue;             // strictly-upper entries are never read
+      double* ptr = A + (size_t)row * npad + col;
+      if (col + 1 <= row) { double2 o = *reinterpret_cast<double2*>(ptr); o.x -= acc[i][j][0]; o.y -= acc[i][j][1]; *reinterpret_cast<double2*>(ptr) = o; }
+      else ptr[0] -= acc[i][j][0];
     }
   }
 }
