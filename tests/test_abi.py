@@ -63,3 +63,22 @@ def test_no_device_fails_loudly():
         solver.Problem(abi.default_config(4, 1.5))
     with pytest.raises(RuntimeError, match="no CPU fallback|no usable CUDA device"):
         solver.depth_apply(abi.default_config(1, 1.5), [1.0], [[1.0, 2.0]])
+
+
+def test_filter_and_builder_fail_loudly_without_a_device():
+    """No CPU fallback anywhere behind the C ABI: on a box without a usable GPU every compute entry point reports
+    RCVD_ERR_NO_DEVICE (skipped where a GPU is present -- the -m gpu tests cover the real calls)."""
+    import numpy as np
+    from robust_cvd_b200 import solver
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a CUDA device is present")
+    except ImportError:
+        pass
+    depth = np.ones((2, 4, 4), np.float32); cams = np.zeros((2, 9), np.float32); cams[:, 6] = 1; cams[:, 7:] = 0.6
+    fl = np.zeros((2, 4, 4, 2), np.float32); mk = np.full((2, 4, 4), 255, np.uint8)
+    with pytest.raises(RuntimeError, match="no usable CUDA device|CUDA"):
+        solver.flow_guided_filter(depth, cams, fl, mk, fl, mk, first_out=0, num_out=2, frame_radius=1)
+    with pytest.raises(RuntimeError, match="no usable CUDA device|CUDA"):
+        solver.build_constraints(np.zeros((2, 4, 4, 3), np.float32), [(0, 1)], fl[:1], mk[:1], 2, 1.0)
