@@ -350,7 +350,17 @@ void DepthFrame::setDepth(const Image& depth) {
   if (depth.type != cvMakeType(CV_32F, 1)) throw std::runtime_error("Depth image has incorrect type.");
   if (stream_.width_ < 0) { stream_.width_ = depth.cols; stream_.height_ = depth.rows; }
   else if (stream_.width_ != depth.cols || stream_.height_ != depth.rows) throw std::runtime_error("Depth frame has inconsistent dimensions.");
-  source_ = std::make_unique<Image>(depth); sourceLoaded_ = true; xformed_.reset();
+  source_ = std::make_unique<Image>(depth); sourceLoaded_ = true; xformed_.reset(); medianValid_ = false;
+}
+float DepthFrame::sourceDepthMedian() {
+  if (!medianValid_) {
+    const Image* d = sourceDepth();
+    if (!d) throw std::runtime_error("Missing depth image.");
+    std::vector<float> s(d->ptr<float>(), d->ptr<float>() + size_t(d->rows) * d->cols);
+    std::nth_element(s.begin(), s.begin() + s.size() / 2, s.end());
+    median_ = s[s.size() / 2]; medianValid_ = true;
+  }
+  return median_;
 }
 void DepthFrame::clear() { clearCache(); intrinsics = Intrinsics(); extrinsics = Extrinsics(); }
 DepthFrame& DepthStream::frame(int i) { if (i < 0 || i >= int(frames_.size())) throw std::runtime_error("Frame index out of range."); return *frames_[i]; }

@@ -165,7 +165,10 @@ class DepthFrame {
   const Image* depth();                // transformed depth (lib/DepthStream.cpp:266-290)
   void setDepth(const Image& depth);   // becomes the new source depth; transformed caches dropped (lib/DepthStream.cpp:102-116)
   void clear();                        // caches + default intrinsics / extrinsics (:145-149)
-  void clearCache() { source_.reset(); sourceLoaded_ = false; xformed_.reset(); }
+  void clearCache() { source_.reset(); sourceLoaded_ = false; xformed_.reset(); medianValid_ = false; }
+  // median of ALL source depth samples incl. zeros, nth_element at size/2 (lib/PoseOptimizer.cpp:1363-1375); cached: the source
+  // depth does not change between the optimisation steps that ask for it
+  float sourceDepthMedian();
   void clearXformedCache() { xformed_.reset(); }
   Xform& depthXform() { return *depthXform_; }
   const Xform& depthXform() const { return *depthXform_; }
@@ -181,7 +184,7 @@ class DepthFrame {
   bool enabled = true;
  private:
   DepthVideo& video_; DepthStream& stream_; int index_;
-  std::unique_ptr<Image> source_, xformed_; bool sourceLoaded_ = false;
+  std::unique_ptr<Image> source_, xformed_; bool sourceLoaded_ = false; bool medianValid_ = false; float median_ = 0.f;
   std::unique_ptr<Xform> depthXform_, spatialXform_;
 };
 class DepthStream {

@@ -71,13 +71,7 @@ DepthVideoPoseOptimizer::ProblemArrays DepthVideoPoseOptimizer::buildProblem(con
   // medians (:1363-1375): over ALL depth samples including zeros, nth_element at size/2
   pa.median.assign(numFrames_, 1.0);
   if (cfg.scale_reg > 0.0) {
-    for (int f : range.frames) {
-      const Image* d = ds.frame(f).sourceDepth();
-      if (!d) throw std::runtime_error("Missing depth image.");
-      std::vector<float> s(d->ptr<float>(), d->ptr<float>() + size_t(d->rows) * d->cols);
-      std::nth_element(s.begin(), s.begin() + s.size() / 2, s.end());
-      pa.median[f] = s[s.size() / 2];
-    }
+    for (int f : range.frames) pa.median[f] = ds.frame(f).sourceDepthMedian();
   }
   // adaptive deformation weights (AdaptiveDeformationCost ctor, :559-619)
   if (cfg.adaptive_deform > 0.0) {
