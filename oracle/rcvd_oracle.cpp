@@ -14,7 +14,10 @@
 // sites cited at each function.  Self-checks: the literal Jet-autodiff
 // evaluation (mirrors DynamicAutoDiffCostFunction<.,4>, lib/PoseOptimizer.cpp:1198)
 // is compared against the independent analytic Jacobians and finite differences
-// in tests/.
+// in tests/.  What IS pinned by reference code that runs here: the camera model / sign / NDC / aspect conventions of
+// StaticSceneCost against the reference's own Python model (utils/geometry.py + loaders/video_dataset.py:177-189, golden
+// tests/golden/ref_python_geometry.npz), the hierarchical2 pair sampler (utils/frame_sampling.py) and the .raw wire format
+// (utils/image_io.py).  The solver semantics remain unpinned.
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/reference
 // legs may load this library.  The product (robust_cvd_b200/) never does.

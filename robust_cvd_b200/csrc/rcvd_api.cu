@@ -1223,12 +1223,22 @@ static int dense_run(const rcvd_config* cfg, int device, const double* params_in
   for (int i = 0; i < nparams; ++i) pv[param_off + i] = params_in[i];
   double* d_p = nullptr; float* d_src = nullptr; void* d_out = nullptr;
   const size_t n = (size_t)w * h;
-  CK(cudaMalloc((void**)&d_p, pv.size() * 8)); CK(cudaMalloc(&d_out, out_bytes));
-  CK(cudaMemcpy(d_p, pv.data(), pv.size() * 8, cudaMemcpyHostToDevice));
-  if (src) { CK(cudaMalloc((void**)&d_src, n * 4)); CK(cudaMemcpy(d_src, src, n * 4, cudaMemcpyHostToDevice)); }
-  k_dense<MODE><<<nblk(n), 256>>>(*cfg, L, d_p, d_src, d_out, h, w);
-  cudaError_t e = cudaMemcpy(out, d_out, out_bytes, cudaMemcpyDeviceToHost);
-  cudaFree(d_p); cudaFree(d_out); if (d_src) cudaFree(d_src);
+  // per-frame calls (DepthFrame::depth(), paramMap, warp for every frame of a video): stream-ordered pool allocations and one
+  // synchronisation instead of three cudaMalloc/cudaFree pairs per call
+  static thread_local cudaStream_t st = nullptr; static thread_local int st_dev = -1;
+  if (!st || st_dev != device) {
+    if (st) cudaStreamDestroy(st);
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); st_dev = device;
+    cudaMemPool_t pool; unsigned long long keep = ~0ull;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  CK(cudaMallocAsync((void**)&d_p, pv.size() * 8, st)); CK(cudaMallocAsync(&d_out, out_bytes, st));
+  CK(cudaMemcpyAsync(d_p, pv.data(), pv.size() * 8, cudaMemcpyHostToDevice, st));
+  if (src) { CK(cudaMallocAsync((void**)&d_src, n * 4, st)); CK(cudaMemcpyAsync(d_src, src, n * 4, cudaMemcpyHostToDevice, st)); }
+  k_dense<MODE><<<nblk(n), 256, 0, st>>>(*cfg, L, d_p, d_src, d_out, h, w);
+  cudaError_t e = cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, st);
+  cudaFreeAsync(d_p, st); cudaFreeAsync(d_out, st); if (d_src) cudaFreeAsync(d_src, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return set_err(RCVD_ERR_CUDA, "dense kernel failed: %s", cudaGetErrorString(e));
   return RCVD_OK;
 }

@@ -89,7 +89,40 @@ def golden_host_restatements():
     np.savez_compressed(os.path.join(HERE, "host_restatement_golden.npz"), **out)
 
 
+def golden_geometry():
+    """Reprojection vectors from the reference's OWN camera model in Python (utils/geometry.py, imported unchanged) with
+    intrinsics / extrinsics assembled exactly like loaders/video_dataset.py:177-189 does from the C++ pose state:
+    extrinsics = [right, up, backward | position], fx = (W/2)/tan(hFov/2), fy = (H/2)/tan(vFov/2), c = (W/2, H/2).
+    The fine-tuning loss consumes the poses the C++ optimiser produced with this model, so StaticSceneCost's geometry
+    (sign conventions, NDC mapping, aspect handling, focal definition) must reproduce it: tests/test_oracle.py checks that the
+    oracle's residuals vanish on these correspondences."""
+    sys.path.insert(0, "/root/reference")
+    import torch
+    from utils import geometry as G
+    from robust_cvd_b200.synthetic import rodrigues
+    rng = np.random.default_rng(21)
+    W, H, K = 64, 48, 160
+    aspect = np.float32(W) / np.float32(H)
+    out = {"W": np.array(W), "H": np.array(H)}
+    aa = rng.normal(0, 0.15, (2, 3)); t = rng.normal(0, 0.3, (2, 3)); phi = np.array([0.26, 0.31])       # tan(vFov/2) per frame
+    extr = np.zeros((2, 3, 4)); intr = np.zeros((2, 4))
+    for f in range(2):
+        extr[f, :, :3] = rodrigues(aa[f]); extr[f, :, 3] = t[f]                                             # columns right, up, backward
+        intr[f] = [(W / 2.0) / (phi[f] * float(aspect)), (H / 2.0) / phi[f], W / 2.0, H / 2.0]
+    px = rng.integers(0, W, K).astype(np.float64); py = rng.integers(0, H, K).astype(np.float64); depth = rng.uniform(1.0, 4.0, K)
+    pixels = torch.tensor(np.stack([px, py])[None, :, None, :]); depths = torch.tensor(depth[None, None, None, :])
+    E = torch.tensor(extr); I = torch.tensor(intr)
+    pc0 = G.pixels_to_points(I[0:1], depths, pixels.clone())
+    pc1 = G.reproject_points(pc0, E[0:1], E[1:2])
+    pix1 = G.project(pc1.clone(), I[1:2])
+    out.update(angle_axis=aa, position=t, tan_half_vfov=phi, px0=px, py0=py, depth0=depth,
+               px1=pix1[0, 0, 0].numpy(), py1=pix1[0, 1, 0].numpy(), depth1=(-pc1[0, 2, 0]).numpy(),
+               world=G.points_cam_to_world(pc0, E[0:1])[0, :, 0].numpy().T)
+    np.savez_compressed(os.path.join(HERE, "ref_python_geometry.npz"), **out)
+
+
 if __name__ == "__main__":
+    golden_geometry()
     golden_pairs()
     golden_solver()
     golden_raw_images()

@@ -216,3 +216,27 @@ def test_dense_constraints_small():
     assert abs(co - cg) <= 1e-10 * abs(co) and np.abs(go - gg).max() <= 1e-8 * max(1.0, np.abs(go).max())
     Ho, Hg = O.normal_matrix_dense(), G.normal_matrix_dense()
     assert np.abs(Ho - Hg).max() <= 1e-9 * np.abs(Ho).max()
+
+
+def test_cuda_residuals_vanish_on_reference_python_correspondences():
+    """tests/golden/ref_python_geometry.npz (reference utils/geometry.py, see tests/test_oracle.py): the CUDA cost of these exact
+    correspondences is zero up to the float32 wire format, for every loss type."""
+    import os
+    from robust_cvd_b200 import solver
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_python_geometry.npz"))
+    W, H = int(g["W"]), int(g["H"]); aspect = float(np.float32(W) / np.float32(H)); n = len(g["px0"])
+    x0, y0 = -1.0 + 2.0 * g["px0"] / W, 1.0 - 2.0 * g["py0"] / H
+    x1, y1 = -1.0 + 2.0 * g["px1"] / W, 1.0 - 2.0 * g["py1"] / H
+    rec = np.concatenate([np.stack([x0, y0, g["depth0"], x1, y1, g["depth1"]], 1), np.stack([x1, y1, g["depth1"], x0, y0, g["depth0"]], 1)]).astype(np.float32)
+    for loss in (abi.LOSS_EUCLIDEAN, abi.LOSS_REPRO_DISPARITY, abi.LOSS_REPRO_DEPTH_RATIO, abi.LOSS_REPRO_LOG_DEPTH):
+        cfg = abi.default_config(2, aspect, depth_type=abi.DEPTH_IDENTITY, static_loss_type=loss, intr_opt=abi.INTR_PER_FRAME,
+                                 scale_reg=0.0, focal_reg=0.0, depth_deform_reg=0.0, spatial_deform_reg=0.0)
+        G = solver.Problem(cfg)
+        G.set_frames(np.ones(2, np.uint8), np.ones(2))
+        G.set_constraints(np.array([[0, 1], [1, 0]], np.int32), np.array([0, n, 2 * n], np.int64), rec)
+        x = np.zeros((2, G.stride)); x[:, 0:3] = g["position"]; x[:, 3:6] = g["angle_axis"]; x[:, 6] = g["tan_half_vfov"]
+        G.set_state(x.ravel())
+        cost = G.evaluate()
+        cost = cost[0] if isinstance(cost, tuple) else cost
+        assert 0.0 <= cost < 2 * n * 3 * (5e-6) ** 2, (loss, cost)
+        G.close()

@@ -157,3 +157,41 @@ def test_hierarchical2_pairs_match_reference_golden():
     g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "hierarchical2_pairs.json")))
     for n, pairs in g.items():
         assert [list(p) for p in synthetic.hierarchical2_pairs(int(n))] == pairs
+
+
+@pytest.mark.parametrize("loss", [abi.LOSS_EUCLIDEAN, abi.LOSS_REPRO_DISPARITY, abi.LOSS_REPRO_DEPTH_RATIO, abi.LOSS_REPRO_LOG_DEPTH])
+def test_static_scene_geometry_against_reference_python_camera_model(loss):
+    """tests/golden/ref_python_geometry.npz: correspondences produced by the reference's own utils/geometry.py
+    (pixels_to_points -> reproject_points -> project, imported unchanged by tests/golden/make_golden.py) with the intrinsics /
+    extrinsics the loader builds from the C++ pose state (loaders/video_dataset.py:177-189).  StaticSceneCost restated in the
+    oracle must see them as exact matches: all three residuals vanish, for every loss type, in both pair directions."""
+    import os
+    from oracle import oracle
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_python_geometry.npz"))
+    W, H = int(g["W"]), int(g["H"])
+    aspect = float(np.float32(W) / np.float32(H))
+    cfg = abi.default_config(2, aspect, depth_type=abi.DEPTH_IDENTITY, static_loss_type=loss, intr_opt=abi.INTR_PER_FRAME,
+                             scale_reg=0.0, focal_reg=0.0, depth_deform_reg=0.0, spatial_deform_reg=0.0)
+    O = oracle.OracleProblem(cfg)
+    n = len(g["px0"])
+    ndc = lambda px, py: (-1.0 + 2.0 * px / W, 1.0 - 2.0 * py / H)          # lib/PoseOptimizer.cpp:104-117 with loc = pixel / size
+    x0, y0 = ndc(g["px0"], g["py0"]); x1, y1 = ndc(g["px1"], g["py1"])
+    fwd = np.stack([x0, y0, g["depth0"], x1, y1, g["depth1"]], 1)
+    bwd = np.stack([x1, y1, g["depth1"], x0, y0, g["depth0"]], 1)
+    rec = np.concatenate([fwd, bwd]).astype(np.float32)
+    O.set_frames(np.ones(2, np.uint8), np.ones(2))
+    O.set_constraints(np.array([[0, 1], [1, 0]], np.int32), np.array([0, n, 2 * n], np.int64), rec)
+    x = np.zeros((2, O.stride))
+    x[:, 0:3] = g["position"]; x[:, 3:6] = g["angle_axis"]; x[:, 6] = g["tan_half_vfov"]
+    O.set_state(x.ravel())
+    r, _ = O.static_jacobian(jac=False)
+    # float32 records (24-byte wire format) bound the agreement: ~1e-7 relative on NDC / depth
+    assert np.abs(r).max() < 5e-6, np.abs(r).max()
+    # and the world point of each observation is the reference's points_cam_to_world
+    if loss == abi.LOSS_EUCLIDEAN:
+        O.set_constraints(np.array([[0, 1]], np.int32), np.array([0, n], np.int64), fwd.astype(np.float32))
+        x2 = x.copy(); x2[1, 0:3] = 0; x2[1, 3:6] = 0; x2[1, 6] = 1.0       # frame 1 at the origin with tan = 1: its point is (ndc*aspect*d, ndc*d, -d)
+        O.set_state(x2.ravel())
+        r2, _ = O.static_jacobian(jac=False)
+        p1 = np.stack([fwd[:, 3] * aspect * fwd[:, 5], fwd[:, 4] * fwd[:, 5], -fwd[:, 5]], 1)
+        np.testing.assert_allclose(p1 - r2.reshape(-1, 3), g["world"], rtol=0, atol=5e-6)   # r = pw1 - pw0
