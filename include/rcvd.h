@@ -219,6 +219,12 @@ int32_t rcvd_depth_param_map(const rcvd_config* cfg, int32_t device, const doubl
 int32_t rcvd_spatial_warp(const rcvd_config* cfg, int32_t device, const double* spatial_params,
                           float* out, int32_t h, int32_t w);
 
+/* Device memory: handles and the one-shot entry points allocate from the device's stream-ordered pool and keep freed blocks
+ * cached (a solve call per schedule step re-uses gigabytes of factor storage).  A host application that shares the GPU with
+ * another allocator (the reference's fine-tuning stage runs PyTorch on it) returns the cache to the driver with this call;
+ * robust_cvd_b200/host does so at the end of every DepthVideoProcessor operation. */
+int32_t rcvd_trim_device_memory(int32_t device);
+
 /* ---- flow-guided temporal depth filter ----
  * Replaces DepthVideoProcessor::flowGuidedFilter (lib/Processor.cpp:315-590) for a consecutive frame range in one call.
  * Arrays are indexed by a local frame index 0..num_frames-1 where index 0 is the absolute frame

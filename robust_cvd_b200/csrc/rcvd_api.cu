@@ -1256,6 +1256,17 @@ RCVD_API int32_t rcvd_spatial_warp(const rcvd_config* cfg, int32_t device, const
   return dense_run<2>(cfg, device, sp, L.ns, L.offS, nullptr, out, (size_t)w * h * 8, h, w);
 }
 
+RCVD_API int32_t rcvd_trim_device_memory(int32_t device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return set_err(RCVD_ERR_NO_DEVICE, "no usable CUDA device");
+  CK(cudaSetDevice(device));
+  CK(cudaDeviceSynchronize());
+  cudaMemPool_t pool;
+  CK(cudaDeviceGetDefaultMemPool(&pool, device));
+  CK(cudaMemPoolTrimTo(pool, 0));
+  return RCVD_OK;
+}
+
 // ---------------------------------------------------------------------------
 // Flow-guided temporal depth filter (rcvd_filter.cuh)
 // ---------------------------------------------------------------------------

@@ -394,6 +394,7 @@ void FlowConstraintsCollection::computeOnDevice() {
     }
     pi += np; ti += nt;
   }
+  rcvd_trim_device_memory(0);
 }
 
 void FlowConstraintsCollection::resetStaticFlag() {

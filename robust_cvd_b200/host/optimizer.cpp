@@ -275,6 +275,7 @@ void DepthVideoPoseOptimizer::poseOptimization(const Params& params, const FlowC
 
 // ---------------------------------------------------------------------------
 void DepthVideoProcessor::process(const Params& params) {   // lib/Processor.cpp:115-144
+  struct Trim { ~Trim() { rcvd_trim_device_memory(0); } } trimAtExit;   // hand the cached device memory back (PyTorch shares the GPU)
   switch (params.op) {
     case Op::None: break;
     case Op::GridXformSplit: gridXformSplit(params); break;
@@ -447,9 +448,11 @@ void DepthVideoProcessor::resetDepthXforms(const Params& params) { video_->depth
 void DepthVideoProcessor::resetSpatialXforms(const Params& params) { video_->depthStream(params.depthStream).resetSpatialXforms(params.spatialXformDesc); }
 void DepthVideoProcessor::normalizeDepth(const Params& params, const FlowConstraintsCollection& constraints) {
   DepthVideoPoseOptimizer optimizer(video_, params.depthStream); optimizer.normalizeDepth(params.poseOptimizer, constraints);
+  rcvd_trim_device_memory(0);
 }
 void DepthVideoProcessor::optimizePoses(const Params& params, const FlowConstraintsCollection& constraints) {
   DepthVideoPoseOptimizer optimizer(video_, params.depthStream); optimizer.poseOptimization(params.poseOptimizer, constraints);
+  rcvd_trim_device_memory(0);   // the solver's cached device memory goes back to the driver: the fine-tuning stage (PyTorch) runs next on this GPU
 }
 
 }  // namespace rcvdh

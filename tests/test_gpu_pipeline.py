@@ -119,6 +119,25 @@ def test_smoothness_loss_through_lib_python(tmp_path):
     np.testing.assert_allclose(xg[:, 7:27], xo.reshape(8, -1)[:, 7:27], rtol=1e-4, atol=1e-7)
 
 
+def test_device_memory_is_returned_after_processor_calls():
+    """rcvd_trim_device_memory: the stream-ordered pool keeps freed blocks cached across solver calls; the host side hands them
+    back after every DepthVideoProcessor operation because the reference's fine-tuning stage (PyTorch) shares the GPU."""
+    import torch
+    from robust_cvd_b200 import solver
+    sc, cfg, pairs, offs, rec, med = helpers.make_case(num_frames=16, depth_type=abi.DEPTH_GRID, depth_grid_x=16, depth_grid_y=12)
+    off_d, nd = helpers.layout_numbers(cfg)
+    solver.lib().rcvd_trim_device_memory(0)
+    free0 = torch.cuda.mem_get_info(0)[0]
+    G = solver.Problem(cfg)
+    helpers.setup_problem(G, cfg, pairs, offs, rec, med, helpers.initial_state(sc, cfg, G.stride, off_d, nd))
+    G.solve(abi.default_solve_options(max_iterations=3))
+    G.close()
+    cached = free0 - torch.cuda.mem_get_info(0)[0]
+    assert cached > 32 << 20                                  # the pool kept the factor storage (~100 MB at npad 208)
+    assert solver.lib().rcvd_trim_device_memory(0) == 0
+    assert free0 - torch.cuda.mem_get_info(0)[0] < cached // 4
+
+
 def test_full_pose_optimization_call(tmp_path):
     """DepthVideoProcessor.optimizePoses with the default 4-step coarse-to-fine schedule in one call."""
     import lib_python as lp
