@@ -238,16 +238,31 @@ def run_ours(args):
         xs = Q.get_state()
         Q.close()
         return s, xs
+    def e2e_once_multi():
+        # N > 1: the handle (and its NCCL communicator) is kept, everything else of a call is redone: host shard -> device,
+        # structure, LM solve with the per-evaluation all-reduces, state back to the host
+        P.set_frames(np.ones(cfg.num_frames, np.uint8), med)
+        P.set_constraints(lp, lo, pinned[0])
+        P.set_state(pinned[1])
+        s = P.solve(opt)
+        return s, P.get_state()
     e2e = None
-    if world == 1 and not args.skip_e2e:
-        e2e_once()
+    if not args.skip_e2e:
+        call = e2e_once if world == 1 else e2e_once_multi
+        call()
         sync_all(); t1 = time.perf_counter(); its = 0
         for _ in range(args.e2e_steps):
-            s, xs = e2e_once(); its += s.iterations
+            s, xs = call(); its += s.iterations
         sync_all(); dt = time.perf_counter() - t1
-        e2e = {"value": C_total * its / dt, "unit": "constraints/s", "h2d_bytes_per_step": int(lr.nbytes + lp.nbytes + lo.nbytes + x0.nbytes + med.nbytes + cfg.num_frames),
-               "d2h_bytes_per_step": int(x0.nbytes), "lm_iterations_per_call": its // max(args.e2e_steps, 1), "ms_per_call": dt * 1e3 / args.e2e_steps,
-               "note": "rcvd_problem_create + set_frames/constraints/state (pinned host) + rcvd_solve + get_state + destroy per call"}
+        h2d = float(lr.nbytes + lp.nbytes + lo.nbytes + x0.nbytes + med.nbytes + cfg.num_frames)
+        if world > 1:
+            tt = torch.tensor([dt, -h2d], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX); dt = float(tt[0].item())
+            hh = torch.tensor([h2d], dtype=torch.float64, device="cuda"); dist.all_reduce(hh, op=dist.ReduceOp.SUM); h2d = float(hh.item())
+        e2e = {"value": C_total * its / dt, "unit": "constraints/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(x0.nbytes) * world, "lm_iterations_per_call": its // max(args.e2e_steps, 1), "ms_per_call": dt * 1e3 / args.e2e_steps,
+               "note": ("rcvd_problem_create + set_frames/constraints/state (pinned host) + rcvd_solve + get_state + destroy per call" if world == 1 else
+                        "per rank: set_frames/constraints/state of its pair shard (pinned host) + rcvd_solve (NCCL all-reduces inside) + get_state on a kept handle/communicator; max over ranks")}
     if rank != 0:
         if dist is not None:
             dist.barrier()
