@@ -1180,6 +1180,41 @@ RCVD_API int32_t rcvd_debug_fp64_tensor_peak(int32_t device, double* tflops) {
   CK(cudaGetLastError());
   *tflops = best; return RCVD_OK;
 }
+// Test / bench hook: parity evidence at the size that is timed.  One LM trust-region step at the current state with the given radius
+// (evaluate, Jacobi scaling, damped factorisation + substitution), then the residual of the linear system on the device:
+//   out[0] = |(S H S + D2) y - S g| / |S g|   (k_spmv_sym over the assembled H, independent of the factorisation kernels)
+//   out[1] = |S g|,  out[2] = cost,  out[3] = |g|_2,  out[4] = |y|_2,  out[5] = non-positive-pivot flag
+__global__ void __launch_bounds__(256) k_lin_residual(const double* __restrict__ S, const double* __restrict__ HSy, const double* __restrict__ D2,
+                                                       const double* __restrict__ y, const double* __restrict__ gs, const double* __restrict__ g,
+                                                       int n, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double r2 = 0.0, b2 = 0.0, g2 = 0.0, y2 = 0.0;
+  if (i < n) { const double r = S[i] * HSy[i] + D2[i] * y[i] - gs[i]; r2 = r * r; b2 = gs[i] * gs[i]; g2 = g[i] * g[i]; y2 = y[i] * y[i]; }
+  r2 = warp_sum(r2); b2 = warp_sum(b2); g2 = warp_sum(g2); y2 = warp_sum(y2);
+  if ((threadIdx.x & 31) == 0) { red_add(out + 0, r2); red_add(out + 1, b2); red_add(out + 2, g2); red_add(out + 3, y2); }
+}
+RCVD_API int32_t rcvd_debug_linear_residual(rcvd_problem* p, double radius, double out[6]) {
+  if (!p || !out || !(radius > 0.0)) return set_err(RCVD_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(p->device));
+  int rc = ensure_ready(p); if (rc) return rc;
+  const int N = p->N, npad = p->L.npad; const size_t Upad = (size_t)N * npad; cudaStream_t st = p->stream;
+  CK(cudaMemsetAsync(p->d_scal, 0, SC_N * sizeof(double), st));
+  CK(cudaMemsetAsync(p->d_fail, 0, sizeof(int), st));
+  if ((rc = enqueue_evaluate(p, p->d_x, true, true, p->d_g, SC_COST))) return rc;
+  k_extract_diag<<<nblk(Upad), 256, 0, st>>>(p->d_H, p->d_diagH, N, npad);
+  k_jacobi_scale<<<nblk(Upad), 256, 0, st>>>(p->d_diagH, p->d_S, (int)Upad, 1);
+  k_lm_prepare<<<nblk(Upad), 256, 0, st>>>(p->d_diagH, p->d_S, p->d_g, p->d_lmdiag, p->d_D2, p->d_gs, (int)Upad, 0, radius, 1e-6, 1e32);
+  if ((rc = factor_solve(p))) return rc;
+  if ((rc = enqueue_model_terms(p))) return rc;                      // leaves H (S y) in d_Hy
+  double* d_out = p->d_scal + 9;                                      // slots 9..12 are unused by the LM loop
+  k_lin_residual<<<nblk(Upad), 256, 0, st>>>(p->d_S, p->d_Hy, p->d_D2, p->d_y, p->d_gs, p->d_g, (int)Upad, d_out);
+  p->launches += 4;
+  if ((rc = read_scalars(p))) return rc;
+  const double r2 = p->h_scal[9], b2 = p->h_scal[10];
+  out[0] = b2 > 0.0 ? std::sqrt(r2 / b2) : std::sqrt(r2); out[1] = std::sqrt(b2); out[2] = p->h_scal[SC_COST];
+  out[3] = std::sqrt(p->h_scal[11]); out[4] = std::sqrt(p->h_scal[12]); out[5] = (double)*p->h_fail;
+  return RCVD_OK;
+}
 RCVD_API int64_t rcvd_launch_count(rcvd_problem* p) { return p ? p->launches : 0; }
 // Test hook: 0 forces the generic accumulate kernel, 1 (default) allows the specialised one.
 // Test / bench hook: elimination-order variant (-1 greedy minimum degree, >= 0 multiple elimination with that degree slack).

@@ -158,6 +158,13 @@ class Problem:
         keys = ["frames", "offdiag_factor_blocks", "levels", "h_blocks", "npad", "stride", "tiles", "update_tasks"]
         return dict(zip(keys, list(out)))
 
+    def linear_residual(self, radius=1e4):
+        """Bench / test hook: one damped LM step at the current state; device-side residual of the linear system and checksums."""
+        out = (C.c_double * 6)()
+        _check(self.L.rcvd_debug_linear_residual(self.h, C.c_double(radius), out))
+        keys = ["rel_residual", "rhs_norm", "cost", "grad_norm", "step_norm", "pivot_fail"]
+        return dict(zip(keys, list(out)))
+
     def profile_linear(self, reps=3):
         """Bench hook: per-kernel-class device time of one factorisation + solve (serialised on one stream, CUDA events per launch)."""
         out = (C.c_double * 8)()
