@@ -224,6 +224,9 @@ int32_t rcvd_spatial_warp(const rcvd_config* cfg, int32_t device, const double* 
  * another allocator (the reference's fine-tuning stage runs PyTorch on it) returns the cache to the driver with this call;
  * robust_cvd_b200/host does so at the end of every DepthVideoProcessor operation. */
 int32_t rcvd_trim_device_memory(int32_t device);
+/* device ordinal the host layer should use: RCVD_DEVICE if set, else the caller's current CUDA device; -1 without a device.
+ * Every entry point restores the caller's current device on return. */
+int32_t rcvd_current_device(void);
 
 /* ---- flow-guided temporal depth filter ----
  * Replaces DepthVideoProcessor::flowGuidedFilter (lib/Processor.cpp:315-590) for a consecutive frame range in one call.
@@ -278,6 +281,18 @@ int32_t rcvd_build_constraints(const rcvd_builder_params* prm, int32_t device, c
                                const int32_t* trip_frames, const float* trip_flow, const uint8_t* trip_mask,
                                int64_t* pair_offsets, float* pair_out, int64_t pair_capacity,
                                int64_t* trip_offsets, float* trip_out, int64_t trip_capacity);
+
+/* Static flags of flow constraints on the device: replaces FlowConstraintsCollection::setStaticFlagFromDynamicMask
+ * (reference lib/FlowConstraints.cpp:573-660) and the distance images of ::dynamicDistance (:257-286).
+ * masks [F][h][w] u8 (dynamic-mask frames: < 127 = dynamic); a constraint is static when
+ * cv::distanceTransform(mask >= 127, DIST_L2, 5) > distance at every end, the end's pixel being
+ * (int(loc.x * w), int(loc.y * w)) -- y scaled by the WIDTH, as the reference does.
+ * pair_locs [n][4] / trip_locs [n][6] float32 in the builder's output layout; *_static one byte per constraint (out);
+ * dist_out optional [F][h][w] float32 distance images. */
+int32_t rcvd_static_flags(int32_t device, const uint8_t* masks, int32_t num_frames, int32_t height, int32_t width, float distance,
+                          int32_t num_pairs, const int32_t* pair_frames, const int64_t* pair_offsets, const float* pair_locs, uint8_t* pair_static,
+                          int32_t num_triplets, const int32_t* trip_frames, const int64_t* trip_offsets, const float* trip_locs, uint8_t* trip_static,
+                          float* dist_out);
 
 #ifdef __cplusplus
 }

@@ -11,6 +11,7 @@ extern "C" {
 int64_t rcvd_launch_count(rcvd_problem* p);
 int64_t rcvd_filter_launch_count(void);
 int64_t rcvd_builder_launch_count(void);
+int64_t rcvd_static_flag_launch_count(void);
 int64_t rcvd_builder_last_rounds(void);          /* selection rounds of the last rcvd_build_constraints call */
 
 /* {frames, off-diagonal factor blocks, levels, H blocks, npad, stride, tiles, update tasks} */
@@ -38,6 +39,7 @@ int32_t rcvd_debug_set_order_slack(rcvd_problem* p, int32_t slack);   /* (4) mul
 int32_t rcvd_debug_set_trim_gemm(rcvd_problem* p, int32_t on);        /* (1) update GEMMs skip the zero padding beyond ceil8(unknowns) */
 int32_t rcvd_debug_set_potrf_chain_warp(rcvd_problem* p, int32_t on); /* (1) warp 0 of k_potrf_smem is dedicated to the pivot chain */
 int32_t rcvd_debug_set_side_slice(rcvd_problem* p, int32_t ctas);     /* (0) grid cap of one overlapped update launch */
+int32_t rcvd_debug_set_update_kernel(rcvd_problem* p, int32_t tma, int32_t side_items_per_cta); /* (1, 0) persistent TMA-fed update kernel / round-1 cp.async kernel; items-per-CTA cap of overlapped launches */
 
 #ifdef __cplusplus
 }

@@ -19,6 +19,7 @@
 
 #include "rcvd_eval.cuh"
 #include "rcvd_linalg.cuh"
+#include "rcvd_update.cuh"
 #include "rcvd_dense.cuh"
 #include "rcvd_filter.cuh"
 #include "rcvd_builder.cuh"
@@ -40,6 +41,15 @@ static int set_err(int code, const char* fmt, ...) {
   g_err = buf; return code;
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return set_err(RCVD_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+// Every entry point works on the device it is given and puts the caller's current device back on exit (the caller may be a PyTorch
+// process working on another GPU of the node).
+struct DevGuard {
+  int prev = -1; cudaError_t err = cudaSuccess;
+  explicit DevGuard(int d) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; err = cudaSetDevice(d); }
+  ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define SET_DEVICE(d) DevGuard dev_guard_(d); if (dev_guard_.err != cudaSuccess) return set_err(RCVD_ERR_CUDA, "cudaSetDevice(%d) failed: %s", (int)(d), cudaGetErrorString(dev_guard_.err))
 
 // ---- NCCL through dlopen (plumbing only; the data path collective is one all-reduce) ----
 namespace nccl {
@@ -175,7 +185,7 @@ __global__ void k_h_to_dense(const double* __restrict__ H, const HBlock* __restr
 }
 
 // ---------------------------------------------------------------------------
-struct Level { int frame_off, nframes; int trsm_off, ntrsm; int upd_off, nupd; int upd2_off, nupd2; int fwd_off, nfwd; };   // upd: targets consumed by the next level; upd2: the rest
+struct Level { int frame_off, nframes; int trsm_off, ntrsm; int upd_off, nupd; int upd2_off, nupd2; int fwd_off, nfwd; int it_off, nit, it2_off, nit2; };   // upd: targets consumed by the next level; upd2: the rest
 
 struct rcvd_problem {
   rcvd_config cfg; Layout L; int N = 0; int device = 0;
@@ -217,6 +227,8 @@ struct rcvd_problem {
   std::vector<void*> allocs;
   // kernel-class profiling (rcvd_debug_profile_linear): when set, enqueue_factor_solve records one event per launch
   std::vector<std::pair<int, cudaEvent_t>>* prof = nullptr;
+  // TMA-fed persistent update kernel (rcvd_update.cuh)
+  UpdItem* d_upd_items = nullptr; CUtensorMap tmapT; bool gemm_tma = true, tmap_ok = false; int upd_rb = 0, upd_neff = 0, num_sms = 148, upd_ipc = 0;
   double upd_flops = 0.0;   // algorithmic flops of the update GEMMs of one factorisation (2 nf^3 per product, nf^2 (nf+1) on symmetric targets)
   rcvd_problem() {}
 };
@@ -335,6 +347,12 @@ static int build_structure(rcvd_problem* p) {
   double upd_flops = 0.0;
   std::vector<int> lvl_frames; std::vector<GemmTask> trsm_tasks, upd_tasks; std::vector<int2> trsm_pairs, upd_pairs;
   std::vector<SolveTask> fwd_tasks, col_tasks; std::vector<int> col_ptr(N + 1, 0); std::vector<TrsmTask> trsm_ll;
+  std::vector<UpdItem> upd_items;
+  // tile cut of the update targets: as few tiles of <= kUpdMaxTile rows as cover the unknowns (rounded to 8), equal sizes
+  const int upd_neff = std::min(npad, (L.nf + 7) / 8 * 8);
+  const int upd_nt = (upd_neff + kUpdMaxTile - 1) / kUpdMaxTile;
+  const int upd_tile = ((upd_neff + upd_nt - 1) / upd_nt + 7) / 8 * 8;
+  p->upd_rb = upd_tile; p->upd_neff = upd_neff;
   p->levels.clear();
   for (int l = 0; l < nl; ++l) {
     Level lv; lv.frame_off = (int)lvl_frames.size(); lv.nframes = (int)lf[l].size();
@@ -369,6 +387,23 @@ static int build_structure(rcvd_problem* p) {
       }
     }
     lv.ntrsm = (int)trsm_tasks.size() - lv.trsm_off; lv.nupd = lv.upd2_off - lv.upd_off; lv.nupd2 = (int)upd_tasks.size() - lv.upd2_off; lv.nfwd = (int)fwd_tasks.size() - lv.fwd_off;
+    // work items of the persistent update kernel: one per (target tile, source-pair list), heaviest first
+    for (int pass = 0; pass < 2; ++pass) {
+      const int t0 = pass ? lv.upd2_off : lv.upd_off, tn = pass ? lv.nupd2 : lv.nupd;
+      const size_t i0 = upd_items.size();
+      for (int q = t0; q < t0 + tn; ++q) {
+        const GemmTask& tk = upd_tasks[q];
+        for (int ti = 0; ti < upd_nt; ++ti) for (int tj = 0; tj < ((tk.lower_only & 1) ? ti + 1 : upd_nt); ++tj) {
+          UpdItem it; it.dst = tk.dst; it.first = tk.first; it.count = tk.count; it.m0 = (short)(ti * upd_tile); it.n0 = (short)(tj * upd_tile);
+          it.mrows = (short)std::min(upd_tile, upd_neff - ti * upd_tile); it.ncols = (short)std::min(upd_tile, upd_neff - tj * upd_tile);
+          it.flags = ((tk.lower_only & 1) && ti == tj) ? 1 : 0;
+          upd_items.push_back(it);
+        }
+      }
+      auto cost = [](const UpdItem& a) { return (long)a.count * (a.mrows / 8) * (a.ncols / 8) * ((a.flags & 1) ? 3 : 4); };
+      std::stable_sort(upd_items.begin() + i0, upd_items.end(), [&](const UpdItem& a, const UpdItem& b) { return cost(a) > cost(b); });
+      if (pass) { lv.it2_off = (int)i0; lv.nit2 = (int)(upd_items.size() - i0); } else { lv.it_off = (int)i0; lv.nit = (int)(upd_items.size() - i0); }
+    }
     p->levels.push_back(lv);
   }
   for (int k = 0; k < N; ++k) { col_ptr[k] = (int)col_tasks.size(); for (int r : cs[k]) col_tasks.push_back({lid[{r, k}] - N, r, k}); }
@@ -380,7 +415,7 @@ static int build_structure(rcvd_problem* p) {
   p->upd_flops = upd_flops;
   UP(p->d_blk_of, blk_of); UP(p->d_hblocks, p->hblocks); UP(p->d_lblocks, lblocks); UP(p->d_lvl_frames, lvl_frames);
   UP(p->d_trsm_tasks, trsm_tasks); UP(p->d_upd_tasks, upd_tasks); UP(p->d_trsm_pairs, trsm_pairs); UP(p->d_upd_pairs, upd_pairs);
-  UP(p->d_fwd_tasks, fwd_tasks); UP(p->d_col_tasks, col_tasks); UP(p->d_col_ptr, col_ptr); UP(p->d_trsm_ll, trsm_ll);
+  UP(p->d_fwd_tasks, fwd_tasks); UP(p->d_col_tasks, col_tasks); UP(p->d_col_ptr, col_ptr); UP(p->d_trsm_ll, trsm_ll); UP(p->d_upd_items, upd_items);
   // tiles
   const int np = (int)(p->pair_frames.size() / 2);
   std::vector<int32_t> tile_pair, tile_count; std::vector<int64_t> tile_begin;
@@ -425,6 +460,26 @@ static int build_structure(rcvd_problem* p) {
   DA(p->d_H, (size_t)p->nHblocks * bs); DA(p->d_Lb, (size_t)(N + nLoff) * bs); DA(p->d_T, (size_t)std::max(nLoff, 1) * bs);
   DA(p->d_invL, (size_t)N * bs); DA(p->d_invT, (size_t)N * npad * 16);
 #undef DA
+  {
+    // 2-D TMA view of the T buffer (off-diagonal factor blocks X_rk, row-major): inner = k, outer = block * npad + row, box [rb][16], 128-B swizzle
+    p->tmap_ok = false;
+    cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, p->device);
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                 CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn && qres == cudaDriverEntryPointSuccess) {
+      const cuuint64_t gdim[2] = {(cuuint64_t)npad, (cuuint64_t)std::max(nLoff, 1) * npad};
+      const cuuint64_t gstr[1] = {(cuuint64_t)npad * sizeof(double)};
+      const cuuint32_t box[2] = {16u, (cuuint32_t)p->upd_rb};
+      const cuuint32_t estr[2] = {1u, 1u};
+      const CUresult r = ((EncodeFn)fn)(&p->tmapT, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, p->d_T, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      p->tmap_ok = (r == CUDA_SUCCESS);
+    }
+    cudaGetLastError();
+    if (p->tmap_ok) CK(cudaFuncSetAttribute(k_update_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem_bytes(p->upd_rb)));
+    else if (p->gemm_tma) return set_err(RCVD_ERR_CUDA, "cuTensorMapEncodeTiled unavailable or failed: the TMA update kernel cannot run");
+  }
   CK(cudaMallocHost((void**)&p->h_scal, (SC_N + 2) * sizeof(double)));
   p->h_fail = (int*)(p->h_scal + SC_N);
   CK(cudaMemsetAsync(p->d_x, 0, U * sizeof(double), p->stream));
@@ -507,6 +562,19 @@ static int enqueue_factor_solve(rcvd_problem* p) {
       CK(cudaEventRecord(p->ev_fork, st)); CK(cudaStreamWaitEvent(side, p->ev_fork, 0));
     }
     if (side_pending) { CK(cudaStreamWaitEvent(st, p->ev_join, 0)); side_pending = false; }   // U2(l-1) before U1(l)
+    auto update = [&](cudaStream_t cs, int off, int n, bool side_launch) {   // persistent TMA-fed update kernel
+      int grid = std::min(n, 2 * p->num_sms);
+      if (side_launch && p->upd_ipc > 0) grid = std::max(grid, (n + p->upd_ipc - 1) / p->upd_ipc);
+      k_update_tma<<<grid, kUpdThreads, upd_smem_bytes(p->upd_rb), cs>>>(p->tmapT, p->d_Lb, p->d_upd_items + off, n, p->d_upd_pairs, npad, p->upd_neff, p->upd_rb);
+    };
+    if (p->gemm_tma) {
+      if (lv.nit > 0) { update(st, lv.it_off, lv.nit, false); p->launches++; mark(P_GEMM); }
+      if (lv.nit2 > 0) {
+        update(p->overlap ? side : st, lv.it2_off, lv.nit2, p->overlap); p->launches++; mark(P_GEMM);
+        if (p->overlap) { CK(cudaEventRecord(p->ev_join, side)); side_pending = true; side_used = true; }
+      }
+      continue;
+    }
     if (lv.nupd > 0) { gemm(st, lv.nupd, p->d_Lb, p->d_T, p->d_T, p->d_upd_tasks + lv.upd_off, p->d_upd_pairs, -1.0, 1.0); p->launches++; mark(P_GEMM); }
     if (lv.nupd2 > 0) {
       cudaStream_t us = p->overlap ? side : st;
@@ -913,7 +981,7 @@ RCVD_API int32_t rcvd_problem_create(const rcvd_config* cfg, int32_t device, rcv
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev)
     return set_err(RCVD_ERR_NO_DEVICE, "no usable CUDA device (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device ordinal out of range");
-  CK(cudaSetDevice(device));
+  SET_DEVICE(device);
   {  // keep freed blocks in the device's default pool (released only on cudaDeviceReset / explicit trim)
     cudaMemPool_t pool; unsigned long long keep = ~0ull;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
@@ -932,7 +1000,7 @@ RCVD_API int32_t rcvd_problem_create(const rcvd_config* cfg, int32_t device, rcv
 }
 RCVD_API void rcvd_problem_destroy(rcvd_problem* p) {
   if (!p) return;
-  cudaSetDevice(p->device);
+  DevGuard dev_guard_(p->device);
   free_all(p);
   for (int i = 0; i < 8; ++i) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
   if (p->comm && nccl::CommDestroy) nccl::CommDestroy(p->comm);
@@ -948,13 +1016,13 @@ RCVD_API int32_t rcvd_problem_set_frames(rcvd_problem* p, const uint8_t* in_rang
   if (median) p->median.assign(median, median + p->N); else p->median.assign(p->N, 1.0);
   if (adaptive && p->cfg.depth_type == RCVD_DEPTH_GRID) p->adaptive.assign(adaptive, adaptive + (size_t)p->N * p->cfg.depth_grid_x * p->cfg.depth_grid_y); else p->adaptive.clear();
   if (p->cfg.adaptive_deform > 0.0 && p->adaptive.empty()) return set_err(RCVD_ERR_INVALID, "adaptive deformation cost requires node weights");
-  if (p->structure_ready) { cudaSetDevice(p->device); cudaStreamSynchronize(p->stream); CK(cudaMemcpy(p->h_state.data(), p->d_x, p->h_state.size() * sizeof(double), cudaMemcpyDeviceToHost)); }
+  if (p->structure_ready) { DevGuard dev_guard_(p->device); cudaStreamSynchronize(p->stream); CK(cudaMemcpy(p->h_state.data(), p->d_x, p->h_state.size() * sizeof(double), cudaMemcpyDeviceToHost)); }
   p->structure_ready = false;
   return RCVD_OK;
 }
 RCVD_API int32_t rcvd_problem_set_constraints(rcvd_problem* p, int32_t np, const int32_t* pf, const int64_t* off, const float* rec) {
   if (!p || np < 0 || (np > 0 && (!pf || !off))) return set_err(RCVD_ERR_INVALID, "bad constraint arrays");
-  if (p->structure_ready) { cudaSetDevice(p->device); cudaStreamSynchronize(p->stream); CK(cudaMemcpy(p->h_state.data(), p->d_x, p->h_state.size() * sizeof(double), cudaMemcpyDeviceToHost)); }
+  if (p->structure_ready) { DevGuard dev_guard_(p->device); cudaStreamSynchronize(p->stream); CK(cudaMemcpy(p->h_state.data(), p->d_x, p->h_state.size() * sizeof(double), cudaMemcpyDeviceToHost)); }
   p->pair_frames.assign(pf, pf + 2 * (size_t)np);
   if (np > 0) p->offsets.assign(off, off + np + 1); else p->offsets.assign(1, 0);
   for (int i = 0; i < np; ++i) {
@@ -969,7 +1037,7 @@ RCVD_API int32_t rcvd_problem_set_constraints(rcvd_problem* p, int32_t np, const
 }
 RCVD_API int32_t rcvd_problem_set_triplets(rcvd_problem* p, int32_t nt, const int32_t* centers, const int64_t* off, const float* rec) {
   if (!p || nt < 0 || (nt > 0 && (!centers || !off))) return set_err(RCVD_ERR_INVALID, "bad triplet arrays");
-  if (p->structure_ready) { cudaSetDevice(p->device); cudaStreamSynchronize(p->stream); CK(cudaMemcpy(p->h_state.data(), p->d_x, p->h_state.size() * sizeof(double), cudaMemcpyDeviceToHost)); }
+  if (p->structure_ready) { DevGuard dev_guard_(p->device); cudaStreamSynchronize(p->stream); CK(cudaMemcpy(p->h_state.data(), p->d_x, p->h_state.size() * sizeof(double), cudaMemcpyDeviceToHost)); }
   p->trip_centers.assign(centers, centers + nt);
   if (nt > 0) p->trip_offsets.assign(off, off + nt + 1); else p->trip_offsets.assign(1, 0);
   for (int i = 0; i < nt; ++i) if (p->trip_offsets[i + 1] < p->trip_offsets[i] || centers[i] < 1 || centers[i] + 1 >= p->N) return set_err(RCVD_ERR_INVALID, "bad triplet group %d", i);
@@ -996,7 +1064,7 @@ RCVD_API int32_t rcvd_problem_init_comm(rcvd_problem* p, int32_t nranks, int32_t
   if (!p || nranks < 1 || rank < 0 || rank >= nranks) return set_err(RCVD_ERR_INVALID, "bad rank/nranks");
   if (nranks == 1) { p->nranks = 1; p->rank = 0; return RCVD_OK; }
   if (!nccl::load()) return set_err(RCVD_ERR_NCCL, "libnccl.so.2 not found");
-  CK(cudaSetDevice(p->device));
+  SET_DEVICE(p->device);
   nccl::UniqueId id; memcpy(id.internal, uid, 128);
   const int r = nccl::CommInitRank(&p->comm, nranks, id, rank);
   if (r != 0) return set_err(RCVD_ERR_NCCL, "ncclCommInitRank failed: %s", nccl::GetErrorString ? nccl::GetErrorString(r) : "?");
@@ -1012,14 +1080,14 @@ RCVD_API int32_t rcvd_problem_get_state(rcvd_problem* p, double* x) {
   if (!p || !x) return set_err(RCVD_ERR_INVALID, "null argument");
   const size_t U = (size_t)p->N * p->L.nf;
   if (!p->structure_ready || p->state_dirty) { if (p->h_state.size() != U) p->h_state.assign(U, 0.0); memcpy(x, p->h_state.data(), U * sizeof(double)); return RCVD_OK; }
-  CK(cudaSetDevice(p->device));
+  SET_DEVICE(p->device);
   CK(cudaMemcpyAsync(x, p->d_x, U * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
   CK(cudaStreamSynchronize(p->stream));
   return RCVD_OK;
 }
 RCVD_API int32_t rcvd_evaluate(rcvd_problem* p, double* cost, double* gradient) {
   if (!p || !cost) return set_err(RCVD_ERR_INVALID, "null argument");
-  CK(cudaSetDevice(p->device));
+  SET_DEVICE(p->device);
   int rc = ensure_ready(p); if (rc) return rc;
   CK(cudaMemsetAsync(p->d_scal, 0, SC_N * sizeof(double), p->stream));
   rc = enqueue_evaluate(p, p->d_x, gradient != nullptr, false, p->d_g, SC_COST); if (rc) return rc;
@@ -1034,7 +1102,7 @@ RCVD_API int32_t rcvd_evaluate(rcvd_problem* p, double* cost, double* gradient) 
 }
 RCVD_API int32_t rcvd_normal_matrix_dense(rcvd_problem* p, double* Hout) {
   if (!p || !Hout) return set_err(RCVD_ERR_INVALID, "null argument");
-  CK(cudaSetDevice(p->device));
+  SET_DEVICE(p->device);
   int rc = ensure_ready(p); if (rc) return rc;
   rc = enqueue_evaluate(p, p->d_x, true, true, p->d_g, SC_COST); if (rc) return rc;
   const size_t U = (size_t)p->N * p->L.nf;
@@ -1051,7 +1119,7 @@ RCVD_API int32_t rcvd_normal_matrix_dense(rcvd_problem* p, double* Hout) {
 // S, D2, b, y: N*stride host doubles.
 RCVD_API int32_t rcvd_debug_linear_solve(rcvd_problem* p, const double* S, const double* D2, const double* b, double* y) {
   if (!p) return set_err(RCVD_ERR_INVALID, "null argument");
-  CK(cudaSetDevice(p->device));
+  SET_DEVICE(p->device);
   int rc = ensure_ready(p); if (rc) return rc;
   rc = enqueue_evaluate(p, p->d_x, true, true, p->d_g, SC_COST); if (rc) return rc;
   const int N = p->N, nf = p->L.nf, npad = p->L.npad; const size_t Upad = (size_t)N * npad;
@@ -1071,7 +1139,7 @@ RCVD_API int32_t rcvd_debug_linear_solve(rcvd_problem* p, const double* S, const
 }
 RCVD_API int32_t rcvd_time_accumulate(rcvd_problem* p, int32_t iters, double* ms) {
   if (!p || iters <= 0) return set_err(RCVD_ERR_INVALID, "bad argument");
-  CK(cudaSetDevice(p->device));
+  SET_DEVICE(p->device);
   int rc = ensure_ready(p); if (rc) return rc;
   for (int i = 0; i < 2; ++i) if (!p->ev[i]) CK(cudaEventCreate(&p->ev[i]));
   if ((rc = enqueue_evaluate(p, p->d_x, true, true, p->d_g, SC_COST))) return rc;   // warm-up
@@ -1084,7 +1152,7 @@ RCVD_API int32_t rcvd_time_accumulate(rcvd_problem* p, int32_t iters, double* ms
 }
 RCVD_API int32_t rcvd_time_iteration(rcvd_problem* p, int32_t iters, double radius, double* ms_iter, double* ms_acc, double* ms_lin, double* ms_cost) {
   if (!p || iters <= 0) return set_err(RCVD_ERR_INVALID, "bad argument");
-  CK(cudaSetDevice(p->device));
+  SET_DEVICE(p->device);
   int rc = ensure_ready(p); if (rc) return rc;
   const int N = p->N, npad = p->L.npad; const size_t Upad = (size_t)N * npad; cudaStream_t st = p->stream;
   for (int i = 0; i < 8; ++i) if (!p->ev[i]) CK(cudaEventCreate(&p->ev[i]));
@@ -1118,7 +1186,7 @@ RCVD_API int32_t rcvd_time_iteration(rcvd_problem* p, int32_t iters, double radi
 RCVD_API int32_t rcvd_debug_profile_linear(rcvd_problem* p, int32_t reps, double out_ms[8]) {
   const bool keep_overlap = reps < 0; if (reps < 0) reps = -reps;
   if (!p || !out_ms || reps == 0) return set_err(RCVD_ERR_INVALID, "bad argument");
-  CK(cudaSetDevice(p->device));
+  SET_DEVICE(p->device);
   int rc = ensure_ready(p); if (rc) return rc;
   const bool ov = p->overlap; if (!keep_overlap) p->overlap = false;
   for (int i = 0; i < 8; ++i) out_ms[i] = 0.0;
@@ -1164,7 +1232,7 @@ RCVD_API int32_t rcvd_debug_fp64_tensor_peak(int32_t device, double* tflops) {
   if (!tflops) return set_err(RCVD_ERR_INVALID, "null argument");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return set_err(RCVD_ERR_NO_DEVICE, "no usable CUDA device");
-  CK(cudaSetDevice(device));
+  SET_DEVICE(device);
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
   const int threads = 512, blocks = prop.multiProcessorCount * 4, iters = 20000;
   double* out = nullptr; CK(cudaMalloc((void**)&out, (size_t)blocks * threads * sizeof(double)));
@@ -1195,7 +1263,7 @@ __global__ void __launch_bounds__(256) k_lin_residual(const double* __restrict__
 }
 RCVD_API int32_t rcvd_debug_linear_residual(rcvd_problem* p, double radius, double out[6]) {
   if (!p || !out || !(radius > 0.0)) return set_err(RCVD_ERR_INVALID, "bad argument");
-  CK(cudaSetDevice(p->device));
+  SET_DEVICE(p->device);
   int rc = ensure_ready(p); if (rc) return rc;
   const int N = p->N, npad = p->L.npad; const size_t Upad = (size_t)N * npad; cudaStream_t st = p->stream;
   CK(cudaMemsetAsync(p->d_scal, 0, SC_N * sizeof(double), st));
@@ -1229,17 +1297,25 @@ RCVD_API int32_t rcvd_debug_set_side_slice(rcvd_problem* p, int32_t ctas) { if (
 RCVD_API int32_t rcvd_debug_set_trim_gemm(rcvd_problem* p, int32_t on) { if (!p) return RCVD_ERR_INVALID; p->trim_gemm = on != 0; if (p->solve_graph) { cudaGraphExecDestroy(p->solve_graph); p->solve_graph = nullptr; } return RCVD_OK; }
 // Test / bench hook: 1 (default) = warp 0 of k_potrf_smem only runs the pivot-tile chain, 0 = it also takes trailing tiles.
 RCVD_API int32_t rcvd_debug_set_potrf_chain_warp(rcvd_problem* p, int32_t on) { if (!p) return RCVD_ERR_INVALID; p->potrf_chain_warp = on != 0; if (p->solve_graph) { cudaGraphExecDestroy(p->solve_graph); p->solve_graph = nullptr; } return RCVD_OK; }
+// Test / bench hook: 1 (default) = persistent TMA-fed update kernel (k_update_tma), 0 = round-1 cp.async kernel (k_gemm_nt).
+RCVD_API int32_t rcvd_debug_set_update_kernel(rcvd_problem* p, int32_t tma, int32_t side_items_per_cta) {
+  if (!p) return RCVD_ERR_INVALID;
+  p->gemm_tma = tma != 0; p->upd_ipc = side_items_per_cta;
+  if (p->solve_graph) { cudaGraphExecDestroy(p->solve_graph); p->solve_graph = nullptr; }
+  if (p->gemm_tma && !p->tmap_ok) p->structure_ready = false;
+  return RCVD_OK;
+}
 RCVD_API int32_t rcvd_debug_set_fast_path(rcvd_problem* p, int32_t on) { if (!p) return RCVD_ERR_INVALID; p->use_fast = on != 0; return RCVD_OK; }
 RCVD_API int32_t rcvd_solve(rcvd_problem* p, const rcvd_solve_options* opt, rcvd_solve_summary* summary) {
   if (!p || !summary) return set_err(RCVD_ERR_INVALID, "null argument");
-  CK(cudaSetDevice(p->device));
+  SET_DEVICE(p->device);
   rcvd_solve_options o; if (opt) o = *opt; else rcvd_default_solve_options(&o);
   return lm_solve(p, o, *summary);
 }
 // Structure statistics (for DESIGN.md / bench): frames, off-diagonal factor blocks, levels, H blocks, npad.
 RCVD_API int32_t rcvd_structure_info(rcvd_problem* p, int32_t out[8]) {
   if (!p) return set_err(RCVD_ERR_INVALID, "null argument");
-  CK(cudaSetDevice(p->device));
+  SET_DEVICE(p->device);
   int rc = ensure_ready(p); if (rc) return rc;
   out[0] = p->N; out[1] = p->nLoff; out[2] = (int)p->levels.size(); out[3] = p->nHblocks; out[4] = p->L.npad; out[5] = p->L.nf; out[6] = p->num_tiles;
   int upd = 0; for (auto& l : p->levels) upd += l.nupd + l.nupd2; out[7] = upd;
@@ -1253,7 +1329,7 @@ static int dense_run(const rcvd_config* cfg, int device, const double* params_in
   if (!cfg || !make_layout(*cfg, L)) return set_err(RCVD_ERR_INVALID, "unsupported transform configuration");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return set_err(RCVD_ERR_NO_DEVICE, "no usable CUDA device; this library has no CPU fallback");
-  CK(cudaSetDevice(device));
+  SET_DEVICE(device);
   std::vector<double> pv(L.nf, 0.0);
   for (int i = 0; i < nparams; ++i) pv[param_off + i] = params_in[i];
   double* d_p = nullptr; float* d_src = nullptr; void* d_out = nullptr;
@@ -1294,12 +1370,24 @@ RCVD_API int32_t rcvd_spatial_warp(const rcvd_config* cfg, int32_t device, const
 RCVD_API int32_t rcvd_trim_device_memory(int32_t device) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return set_err(RCVD_ERR_NO_DEVICE, "no usable CUDA device");
-  CK(cudaSetDevice(device));
+  SET_DEVICE(device);
   CK(cudaDeviceSynchronize());
   cudaMemPool_t pool;
   CK(cudaDeviceGetDefaultMemPool(&pool, device));
   CK(cudaMemPoolTrimTo(pool, 0));
+  unsigned long long none = 0;                       // rcvd_problem_create raises the threshold again for the next solve
+  cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &none);
   return RCVD_OK;
+}
+// The device the host layer should work on: RCVD_DEVICE if set, else the caller's current CUDA device (so that a process launched
+// per GPU -- torchrun LOCAL_RANK + torch.cuda.set_device -- lands on its own GPU); -1 without a usable device.
+RCVD_API int32_t rcvd_current_device(void) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return -1; }
+  if (const char* e = getenv("RCVD_DEVICE")) { const int d = atoi(e); return (d >= 0 && d < ndev) ? d : -1; }
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return d;
 }
 
 // ---------------------------------------------------------------------------
@@ -1319,7 +1407,7 @@ RCVD_API int32_t rcvd_flow_guided_filter(const rcvd_filter_params* prm, int32_t 
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev)
     return set_err(RCVD_ERR_NO_DEVICE, "no usable CUDA device (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device ordinal out of range");
-  CK(cudaSetDevice(device));
+  SET_DEVICE(device);
   const int F = q.num_frames; const size_t plane = (size_t)q.width * q.height, dplane = (size_t)q.depth_width * q.depth_height;
   // cameras: tan(fov / 2) in float on the host, like DepthVideo::project (lib/DepthVideo.cpp:640-641)
   std::vector<float> hc((size_t)F * 12, 0.f);
@@ -1339,8 +1427,10 @@ RCVD_API int32_t rcvd_flow_guided_filter(const rcvd_filter_params* prm, int32_t 
   for (int f = 0; f < F; ++f) { maxfar = std::max(maxfar, far_begin[f + 1]); far_begin[f + 1] += far_begin[f]; }
   { std::vector<int> cur(far_begin.begin(), far_begin.end() - 1); for (int k = 0; k < q.num_far; ++k) order[cur[far_pairs[2 * k]]++] = k; }
   cudaStream_t st; CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  std::vector<void*> bufs;
-  auto dev = [&](size_t bytes) -> void* { void* ptr = nullptr; if (cudaMallocAsync(&ptr, std::max<size_t>(bytes, 16), st) != cudaSuccess) return nullptr; bufs.push_back(ptr); return ptr; };
+  std::vector<void*> bufs; bool ok = true;
+  // a failed allocation must be seen before anything is launched on null buffers (an illegal address is a sticky context error,
+  // and PyTorch shares this context)
+  auto dev = [&](size_t bytes) -> void* { void* ptr = nullptr; if (cudaMallocAsync(&ptr, std::max<size_t>(bytes, 16), st) != cudaSuccess) { ok = false; cudaGetLastError(); return nullptr; } bufs.push_back(ptr); return ptr; };
   auto up = [&](const void* src, size_t bytes) -> void* { void* d = dev(bytes); if (d && src && bytes) cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st); return d; };
   FilterArgs a{};
   a.depth = (const float*)up(depth, (size_t)F * dplane * 4);
@@ -1363,18 +1453,25 @@ RCVD_API int32_t rcvd_flow_guided_filter(const rcvd_filter_params* prm, int32_t 
   a.out = (float*)dev((size_t)q.num_out * plane * 4);
   const int win = 2 * q.spatial_radius + 1;
   a.max_samples = win * win * (1 + 2 * q.frame_radius + maxfar);
-  if (q.median) a.scratch = (float2*)dev((size_t)q.num_out * plane * a.max_samples * sizeof(float2));
-  bool ok = true; for (void* b : bufs) ok = ok && b != nullptr;
+  // the weighted median sorts a per-pixel sample row: the scratch is bounded to ~1 GiB by filtering the range in frame chunks
+  const size_t per_frame_scratch = plane * (size_t)a.max_samples * sizeof(float2);
+  const int chunk = q.median ? (int)std::max<size_t>(1, std::min<size_t>((size_t)q.num_out, ((size_t)1 << 30) / std::max<size_t>(per_frame_scratch, 1))) : q.num_out;
+  if (q.median) a.scratch = (float2*)dev((size_t)chunk * per_frame_scratch);
   int rc = RCVD_OK;
   if (!ok) rc = set_err(RCVD_ERR_CUDA, "device allocation failed in rcvd_flow_guided_filter");
   else {
     cudaMemsetAsync(a.out, 0, (size_t)q.num_out * plane * 4, st);
-    a.F = F; a.first_out = q.first_out; a.num_out = q.num_out; a.last_frame = q.first_out + q.num_out - 1;
+    float* const out_dev = a.out;
+    a.F = F; a.last_frame = q.first_out + q.num_out - 1;
     a.w = q.width; a.h = q.height; a.wd = q.depth_width; a.hd = q.depth_height;
     a.frame_radius = q.frame_radius; a.spatial_radius = q.spatial_radius; a.median = q.median; a.inv_aspect = q.inv_aspect;
-    const dim3 grid((q.width + 31) / 32, (q.height + 3) / 4, q.num_out);
-    if (q.median) k_flow_guided_filter<true><<<grid, 128, 0, st>>>(a); else k_flow_guided_filter<false><<<grid, 128, 0, st>>>(a);
-    g_filter_launches++;
+    for (int c0 = 0; c0 < q.num_out; c0 += chunk) {
+      a.first_out = q.first_out + c0; a.num_out = std::min(chunk, q.num_out - c0); a.out = out_dev + (size_t)c0 * plane;
+      const dim3 grid((q.width + 31) / 32, (q.height + 3) / 4, a.num_out);
+      if (q.median) k_flow_guided_filter<true><<<grid, 128, 0, st>>>(a); else k_flow_guided_filter<false><<<grid, 128, 0, st>>>(a);
+      g_filter_launches++;
+    }
+    a.out = out_dev;
     e = cudaMemcpyAsync(out, a.out, (size_t)q.num_out * plane * 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) rc = set_err(RCVD_ERR_CUDA, "flow-guided filter failed: %s", cudaGetErrorString(e));
@@ -1412,7 +1509,7 @@ RCVD_API int32_t rcvd_build_constraints(const rcvd_builder_params* prm, int32_t 
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev)
     return set_err(RCVD_ERR_NO_DEVICE, "no usable CUDA device (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device ordinal out of range");
-  CK(cudaSetDevice(device));
+  SET_DEVICE(device);
   const size_t plane = (size_t)q.width * q.height, FP = plane * F;
   cudaStream_t st; CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   std::vector<void*> bufs; bool ok = true;
@@ -1421,7 +1518,7 @@ RCVD_API int32_t rcvd_build_constraints(const rcvd_builder_params* prm, int32_t 
   auto cleanup = [&]() { for (void* b : bufs) cudaFreeAsync(b, st); cudaStreamSynchronize(st); cudaStreamDestroy(st); };
   // ---- corner scores of every frame ----
   float* d_bgr = (float*)up(color_bgr, FP * 3 * sizeof(float));
-  float* d_gray = (float*)dev(FP * 4), *d_pl = (float*)dev(FP * 12), *d_tmp = (float*)dev(FP * 12), *d_corner = (float*)dev(FP * 4);
+  float* d_gray = (float*)dev(FP * 4), *d_pl = (float*)dev(FP * 12), *d_corner = (float*)dev(FP * 4); double* d_tmp = (double*)dev(FP * 24);
   BuilderArgs a{};
   a.dyn = dyn_dist ? (const float*)up(dyn_dist, (size_t)F * q.dyn_width * q.dyn_height * 4) : nullptr;
   a.pair_frames = (const int*)up(pair_frames, (size_t)P * 8); a.pair_flow = (const float*)up(pair_flow, (size_t)P * plane * 8); a.pair_mask = (const uint8_t*)up(pair_mask, (size_t)P * plane);
@@ -1433,7 +1530,7 @@ RCVD_API int32_t rcvd_build_constraints(const rcvd_builder_params* prm, int32_t 
   k_gray<<<(unsigned)((FP + 255) / 256), 256, 0, st>>>(d_bgr, d_gray, FP);
   k_sobel_products<<<(unsigned)((FP + 255) / 256), 256, 0, st>>>(d_gray, d_pl, F, H, W);
   k_box_h<<<(unsigned)((FP * 3 + 255) / 256), 256, 0, st>>>(d_pl, d_tmp, (size_t)3 * F * H, W);
-  k_box_v_eig<<<(unsigned)((FP + 255) / 256), 256, 0, st>>>(d_tmp, d_corner, F, H, W);
+  k_box_v_eig<<<(unsigned)(((size_t)F * W + 127) / 128), 128, 0, st>>>(d_tmp, d_corner, F, H, W);
   g_builder_launches += 4;
   a.corner = d_corner; a.P = P; a.T = T; a.h = H; a.w = W; a.dh = q.dyn_height; a.dw = q.dyn_width; a.sep = q.match_separation; a.min_dyn = q.min_dynamic_distance;
   // dynamic-mask scale (lib/FlowConstraints.cpp:415-417); without a dynamic mask the distance image has the colour size (:277-285)
@@ -1459,7 +1556,9 @@ RCVD_API int32_t rcvd_build_constraints(const rcvd_builder_params* prm, int32_t 
   cudaMemsetAsync(d_cnt, 0, (size_t)(2 * I + 2) * 8, st);
   k_count_accepted<<<dim3(gx, I), 256, 0, st>>>(a, d_cnt + 1); g_builder_launches++;
   std::vector<unsigned long long> cnt(I), off(I + 1, 0);
-  CK(cudaMemcpyAsync(cnt.data(), d_cnt + 1, (size_t)I * 8, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+  e = cudaMemcpyAsync(cnt.data(), d_cnt + 1, (size_t)I * 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { cleanup(); return set_err(RCVD_ERR_CUDA, "constraint count read-back failed: %s", cudaGetErrorString(e)); }
   for (int i = 0; i < I; ++i) off[i + 1] = off[i] + cnt[i];
   const unsigned long long pair_total = off[P], total = off[I];
   for (int i = 0; i < P; ++i) pair_offsets[i + 1] = (int64_t)off[i + 1];
@@ -1496,4 +1595,54 @@ RCVD_API int32_t rcvd_build_constraints(const rcvd_builder_params* prm, int32_t 
   }
   cleanup();
   return rc;
+}
+
+// ---------------------------------------------------------------------------
+// Dynamic-mask distance transform + static flags on the device (rcvd_builder.cuh)
+// ---------------------------------------------------------------------------
+static int64_t g_flag_launches = 0;
+RCVD_API int64_t rcvd_static_flag_launch_count() { return g_flag_launches; }
+// dist_out (optional): [F][h][w] float32 = cv::distanceTransform(mask >= 127 ? 255 : 0, DIST_L2, 5) of every frame (fixed-point chamfer).
+// pair_static / trip_static (optional): one byte per constraint.
+RCVD_API int32_t rcvd_static_flags(int32_t device, const uint8_t* masks, int32_t F, int32_t h, int32_t w, float distance,
+                                   int32_t num_pairs, const int32_t* pair_frames, const int64_t* pair_offsets, const float* pair_locs, uint8_t* pair_static,
+                                   int32_t num_triplets, const int32_t* trip_frames, const int64_t* trip_offsets, const float* trip_locs, uint8_t* trip_static,
+                                   float* dist_out) {
+  if (!masks || F <= 0 || h <= 0 || w <= 0 || num_pairs < 0 || num_triplets < 0) return set_err(RCVD_ERR_INVALID, "bad static-flag arguments");
+  if ((num_pairs > 0 && (!pair_frames || !pair_offsets || !pair_static)) || (num_triplets > 0 && (!trip_frames || !trip_offsets || !trip_static))) return set_err(RCVD_ERR_INVALID, "null argument");
+  for (int i = 0; i < num_pairs; ++i) if (pair_frames[2 * i] < 0 || pair_frames[2 * i] >= F || pair_frames[2 * i + 1] < 0 || pair_frames[2 * i + 1] >= F || pair_offsets[i + 1] < pair_offsets[i]) return set_err(RCVD_ERR_INVALID, "bad pair %d", i);
+  for (int i = 0; i < num_triplets; ++i) if (trip_frames[i] < 1 || trip_frames[i] + 1 >= F || trip_offsets[i + 1] < trip_offsets[i]) return set_err(RCVD_ERR_INVALID, "bad triplet %d", i);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev)
+    return set_err(RCVD_ERR_NO_DEVICE, "no usable CUDA device (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device ordinal out of range");
+  SET_DEVICE(device);
+  const size_t plane = (size_t)w * h;
+  cudaStream_t st; CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  std::vector<void*> bufs; bool ok = true;
+  auto dev = [&](size_t bytes) -> void* { void* ptr = nullptr; if (cudaMallocAsync(&ptr, std::max<size_t>(bytes, 16), st) != cudaSuccess) { ok = false; cudaGetLastError(); return nullptr; } bufs.push_back(ptr); return ptr; };
+  auto up = [&](const void* src, size_t bytes) -> void* { void* d = dev(bytes); if (d && src && bytes) cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st); return d; };
+  auto cleanup = [&]() { for (void* b : bufs) cudaFreeAsync(b, st); cudaStreamSynchronize(st); cudaStreamDestroy(st); };
+  const uint8_t* d_masks = (const uint8_t*)up(masks, (size_t)F * plane);
+  unsigned* d_scratch = (unsigned*)dev((size_t)F * plane * 4); float* d_dist = (float*)dev((size_t)F * plane * 4);
+  const int64_t np_total = num_pairs ? pair_offsets[num_pairs] : 0, nt_total = num_triplets ? trip_offsets[num_triplets] : 0;
+  std::vector<int32_t> pf3((size_t)num_pairs * 3, -1), tf3((size_t)num_triplets * 3, -1);
+  for (int i = 0; i < num_pairs; ++i) { pf3[3 * i] = pair_frames[2 * i]; pf3[3 * i + 1] = pair_frames[2 * i + 1]; }
+  for (int i = 0; i < num_triplets; ++i) { tf3[3 * i] = trip_frames[i] - 1; tf3[3 * i + 1] = trip_frames[i]; tf3[3 * i + 2] = trip_frames[i] + 1; }
+  int* d_pf = (int*)up(pf3.data(), pf3.size() * 4); int* d_tf = (int*)up(tf3.data(), tf3.size() * 4);
+  long long* d_po = (long long*)up(pair_offsets, (size_t)(num_pairs + 1) * 8 * (num_pairs > 0)); long long* d_to = (long long*)up(trip_offsets, (size_t)(num_triplets + 1) * 8 * (num_triplets > 0));
+  float* d_pl = (float*)up(pair_locs, (size_t)np_total * 16); float* d_tl = (float*)up(trip_locs, (size_t)nt_total * 24);
+  uint8_t* d_ps = (uint8_t*)dev((size_t)np_total); uint8_t* d_ts = (uint8_t*)dev((size_t)nt_total);
+  if (!ok) { cleanup(); return set_err(RCVD_ERR_CUDA, "device allocation failed in rcvd_static_flags"); }
+  k_chamfer5<<<F, kChamThreads, 0, st>>>(d_masks, d_scratch, d_dist, h, w); g_flag_launches++;
+  if (np_total > 0) { k_static_flags<<<dim3(8, num_pairs), 256, 0, st>>>(d_dist, h, w, distance, 2, d_pf, d_po, num_pairs, d_pl, d_ps); g_flag_launches++; }
+  if (nt_total > 0) { k_static_flags<<<dim3(8, num_triplets), 256, 0, st>>>(d_dist, h, w, distance, 3, d_tf, d_to, num_triplets, d_tl, d_ts); g_flag_launches++; }
+  if (np_total > 0) cudaMemcpyAsync(pair_static, d_ps, (size_t)np_total, cudaMemcpyDeviceToHost, st);
+  if (nt_total > 0) cudaMemcpyAsync(trip_static, d_ts, (size_t)nt_total, cudaMemcpyDeviceToHost, st);
+  if (dist_out) cudaMemcpyAsync(dist_out, d_dist, (size_t)F * plane * 4, cudaMemcpyDeviceToHost, st);
+  e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  cleanup();
+  if (e != cudaSuccess) return set_err(RCVD_ERR_CUDA, "static-flag kernels failed: %s", cudaGetErrorString(e));
+  return RCVD_OK;
 }

@@ -3,8 +3,10 @@
 // Restates FlowConstraintsCollection::compute for pairs and triplets (reference lib/FlowConstraints.cpp:401-550) and the
 // greedy disc sampler sampleConstraints (:352-397) for a whole batch of frame pairs / triplets at once:
 //   1. k_gray / k_sobel_products / k_box_h / k_box_v_eig : cv::cvtColor(BGR2GRAY) + cv::cornerMinEigenVal(blockSize 3,
-//      ksize 3, BORDER_REFLECT_101) per source frame, float32 with the operation order of the OpenCV restatement in
-//      robust_cvd_b200/host/constraints.cpp (explicit _rn intrinsics: no FMA contraction), bit-exact with it;
+//      ksize 3, BORDER_REFLECT_101) per source frame in the exact operation order of OpenCV 4.13's AVX2 code paths
+//      (found by search against cv2, tests/test_host.py): fused multiply-adds where OpenCV's universal intrinsics use
+//      v_fma / v_muladd, the box sum in double like cv::boxFilter's CV_64F accumulator, everything else unfused float
+//      (explicit _rn intrinsics) -- np.array_equal with cv2.cornerMinEigenVal and with robust_cvd_b200/host/constraints.cpp;
 //   2. k_pair_candidates / k_triplet_candidates : the per-pixel admission tests (:427-457, :497-541), writing a per-item
 //      priority plane (corner score) and state plane (0 candidate, 2 not a candidate);
 //   3. k_select_round : the sequential sampler "sort by score, accept a pixel unless an accepted one lies within the disc"
@@ -26,56 +28,172 @@ __device__ __forceinline__ int reflect101(int p, int n) {
   return p;
 }
 
-// gray = b*0.114f + g*0.587f + r*0.299f, left to right
+// cv::cvtColor(BGR2GRAY), CV_32F: fma(r, 0.299f, fma(b, 0.114f, g * 0.587f))  (RGB2Gray<float> SIMD body)
 __global__ void __launch_bounds__(256) k_gray(const float* __restrict__ bgr, float* __restrict__ gray, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float b = bgr[3 * i], g = bgr[3 * i + 1], r = bgr[3 * i + 2];
-  gray[i] = __fadd_rn(__fadd_rn(__fmul_rn(b, 0.114f), __fmul_rn(g, 0.587f)), __fmul_rn(r, 0.299f));
+  gray[i] = __fmaf_rn(r, 0.299f, __fmaf_rn(b, 0.114f, __fmul_rn(g, 0.587f)));
 }
 
-// Sobel derivatives (scaled by 1/12) and their products; planes[0..2] = dx*dx, dx*dy, dy*dy
+// Sobel derivatives (scale 1/12 folded into the smoothing kernel, cv::Sobel) and their products; planes[0..2] = dx*dx, dx*dy, dy*dy.
+//   dx: row [-1 0 1] unscaled, column [s 2s s]:  fma(rd[y-1] + rd[y+1], s, rd[y] * 2s)         (SymmColumnSmallVec_32f)
+//   dy: row [s 2s s]: fma(M, 2s, (L + R) * s) in the vector body, fma(L + R, s, M * 2s) in the scalar tail x >= 4 floor(w / 4)
+//       (SymmRowSmallVec_32f / the compiler-contracted scalar loop), column [-1 0 1]: rs[y+1] - rs[y-1]
 __global__ void __launch_bounds__(256) k_sobel_products(const float* __restrict__ gray, float* __restrict__ planes, int F, int h, int w) {
   const size_t plane = (size_t)w * h, i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= plane * F) return;
   const int f = (int)(i / plane), p = (int)(i % plane), y = p / w, x = p % w;
   const float* G = gray + (size_t)f * plane;
   const float scale = 1.f / 12.f, scale2 = __fmul_rn(2.f, scale);
+  const bool tail = x >= (w & ~3);
   float rd[3], rs[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const int yy = reflect101(y + k - 1, h);
     const float a = G[(size_t)yy * w + reflect101(x - 1, w)], b = G[(size_t)yy * w + x], c = G[(size_t)yy * w + reflect101(x + 1, w)];
     rd[k] = __fsub_rn(c, a);
-    rs[k] = __fadd_rn(__fadd_rn(a, c), __fmul_rn(b, 2.f));
+    const float lr = __fadd_rn(a, c);
+    rs[k] = tail ? __fmaf_rn(lr, scale, __fmul_rn(b, scale2)) : __fmaf_rn(b, scale2, __fmul_rn(lr, scale));
   }
-  const float dx = __fadd_rn(__fmul_rn(__fadd_rn(rd[0], rd[2]), scale), __fmul_rn(rd[1], scale2));
-  const float dy = __fmul_rn(__fsub_rn(rs[2], rs[0]), scale);
+  const float dx = __fmaf_rn(__fadd_rn(rd[0], rd[2]), scale, __fmul_rn(rd[1], scale2));
+  const float dy = __fsub_rn(rs[2], rs[0]);
   const size_t FP = plane * F;
   planes[i] = __fmul_rn(dx, dx); planes[FP + i] = __fmul_rn(dx, dy); planes[2 * FP + i] = __fmul_rn(dy, dy);
 }
-// 3x1 box sum of the three product planes (normalize = false), then 1x3 + min eigenvalue
-__global__ void __launch_bounds__(256) k_box_h(const float* __restrict__ in, float* __restrict__ out, size_t rows, int w) {   // rows = 3*F*h
+// 3x3 box sum of the three product planes (normalize = false): cv::boxFilter accumulates CV_32F input in double and rounds once --
+// horizontal pass (RowSum, ksize 3: (a + b) + c in double), then the sliding vertical pass + min eigenvalue
+__global__ void __launch_bounds__(256) k_box_h(const float* __restrict__ in, double* __restrict__ out, size_t rows, int w) {   // rows = 3*F*h
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * w) return;
   const size_t r = i / w; const int x = (int)(i % w);
   const float* R = in + r * w;
-  out[i] = __fadd_rn(__fadd_rn(R[reflect101(x - 1, w)], R[x]), R[reflect101(x + 1, w)]);
+  out[i] = ((double)R[reflect101(x - 1, w)] + (double)R[x]) + (double)R[reflect101(x + 1, w)];
 }
-__global__ void __launch_bounds__(256) k_box_v_eig(const float* __restrict__ tmp, float* __restrict__ score, int F, int h, int w) {
-  const size_t plane = (size_t)w * h, i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= plane * F) return;
-  const int f = (int)(i / plane), p = (int)(i % plane), y = p / w, x = p % w;
+// Vertical pass exactly like cv::boxFilter's ColumnSum<double, float>: a running column sum SUM = rows[y-1] + rows[y] slides down the
+// image (s0 = SUM + rows[y+1]; out = float(s0); SUM = s0 - rows[y-1]).  The double additions are almost always exact, but when the nine
+// products sum to an exact float tie the last bit of the running double decides the rounding, so the recurrence is kept: one thread per
+// (frame, column) walks the rows (loads coalesced across columns), three planes at once, and finishes with the min-eigenvalue formula.
+__global__ void __launch_bounds__(128) k_box_v_eig(const double* __restrict__ tmp, float* __restrict__ score, int F, int h, int w) {
+  const size_t plane = (size_t)w * h;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= F * w) return;
+  const int f = i / w, x = i % w;
   const size_t FP = plane * F;
-  float b3[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const float* T = tmp + k * FP + (size_t)f * plane;
-    b3[k] = __fadd_rn(__fadd_rn(T[(size_t)reflect101(y - 1, h) * w + x], T[(size_t)y * w + x]), T[(size_t)reflect101(y + 1, h) * w + x]);
+  const double* T0 = tmp + (size_t)f * plane + x; const double* T1 = T0 + FP; const double* T2 = T1 + FP;
+  const size_t rm = (size_t)reflect101(-1, h) * w;
+  double s[3] = {T0[rm] + T0[0], T1[rm] + T1[0], T2[rm] + T2[0]};
+  for (int y = 0; y < h; ++y) {
+    const size_t rn = (size_t)reflect101(y + 1, h) * w, ro = (size_t)reflect101(y - 1, h) * w;
+    const double a0 = s[0] + T0[rn], a1 = s[1] + T1[rn], a2 = s[2] + T2[rn];
+    s[0] = a0 - T0[ro]; s[1] = a1 - T1[ro]; s[2] = a2 - T2[ro];
+    const float a = __fmul_rn((float)a0, 0.5f), b = (float)a1, c = __fmul_rn((float)a2, 0.5f);
+    const float d = __fsub_rn(a, c);
+    score[(size_t)f * plane + (size_t)y * w + x] = __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(b, b))));
   }
-  const float a = __fmul_rn(b3[0], 0.5f), b = b3[1], c = __fmul_rn(b3[2], 0.5f);
-  const float d = __fsub_rn(a, c);
-  score[i] = __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(b, b))));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Static flags (reference FlowConstraintsCollection::setStaticFlagFromDynamicMask, lib/FlowConstraints.cpp:573-660, and
+// dynamicDistance, :257-286): cv::distanceTransform(mask >= 127, DIST_L2, 5) per frame, then every constraint end looks its
+// distance up.  OpenCV's 5x5 chamfer is a sequential two-pass scan in 16.16 fixed point; its in-row recurrence
+//     d[x] = min(c[x], d[x-1] + 1.0)      (c[x]: candidates from the two rows above, already final)
+// is a prefix minimum of c[k] - k * 1.0 (integers: associative, so the parallel scan is bit-identical to the sequential loop);
+// rows stay sequential.  One CTA per frame, 256 columns per scan step, the forward values kept in a global scratch plane.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr unsigned kChamHV = 65536u;
+constexpr int kChamThreads = 256;
+
+// inclusive prefix minimum over the block (thread order), combined with `carry` (minimum of everything before this chunk);
+// returns the prefix value of this thread; carry is updated to include the whole chunk.  warp_sm: >= 8 ints of shared memory.
+__device__ __forceinline__ int block_prefix_min(int v, int* warp_sm, int& carry) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v = min(v, t); }
+  if (lane == 31) warp_sm[wid] = v;
+  __syncthreads();
+  int before = carry;
+  for (int q = 0; q < wid; ++q) before = min(before, warp_sm[q]);
+  int total = carry;
+  for (int q = 0; q < kChamThreads / 32; ++q) total = min(total, warp_sm[q]);
+  __syncthreads();
+  carry = total;
+  return min(v, before);
+}
+
+__global__ void __launch_bounds__(kChamThreads) k_chamfer5(const uint8_t* __restrict__ masks, unsigned* __restrict__ scratch, float* __restrict__ dist, int h, int w) {
+  __shared__ int warp_sm[kChamThreads / 32];
+  const unsigned DIAG = (unsigned)(1.4f * 65536.f + 0.5f), LONGW = (unsigned)(2.1969f * 65536.f + 0.5f);
+  const unsigned INIT = 0x7fffffffu >> 2, DMAX = 0x7fffffffu - (1u << 16);
+  const size_t plane = (size_t)w * h;
+  const uint8_t* M = masks + blockIdx.x * plane;
+  unsigned* T = scratch + blockIdx.x * plane;
+  float* D = dist + blockIdx.x * plane;
+  auto at = [&](int y, int x) -> unsigned { return (y < 0 || y >= h || x < 0 || x >= w) ? INIT : T[(size_t)y * w + x]; };
+  // forward pass (top-left to bottom-right)
+  for (int y = 0; y < h; ++y) {
+    int carry = (int)(INIT + kChamHV);                 // d[-1] = INIT in the shifted domain: INIT - (-1) * HV
+    for (int c0 = 0; c0 < w; c0 += kChamThreads) {
+      const int x = c0 + threadIdx.x;
+      int v = 0x7fffffff;
+      if (x < w) {
+        unsigned c = 0;
+        if (M[(size_t)y * w + x] >= 127) {               // dynamicDistance binarises the mask: < 127 -> 0 (dynamic), else 255
+          c = at(y - 2, x - 1) + LONGW;
+          c = min(c, at(y - 2, x + 1) + LONGW); c = min(c, at(y - 1, x - 2) + LONGW); c = min(c, at(y - 1, x - 1) + DIAG);
+          c = min(c, at(y - 1, x) + kChamHV); c = min(c, at(y - 1, x + 1) + DIAG); c = min(c, at(y - 1, x + 2) + LONGW);
+        }
+        v = (int)c - x * (int)kChamHV;
+      }
+      const int pm = block_prefix_min(v, warp_sm, carry);
+      if (x < w) T[(size_t)y * w + x] = (unsigned)(pm + x * (int)kChamHV);
+    }
+    __syncthreads();                                     // row y visible to the whole block before row y + 1 reads it
+  }
+  // backward pass (bottom-right to top-left), mirrored column index j = w - 1 - x
+  const float scale = 1.f / 65536.f;
+  for (int y = h - 1; y >= 0; --y) {
+    int carry = (int)(INIT + kChamHV);
+    for (int c0 = 0; c0 < w; c0 += kChamThreads) {
+      const int j = c0 + threadIdx.x, x = w - 1 - j;
+      int v = 0x7fffffff;
+      if (j < w) {
+        unsigned c = T[(size_t)y * w + x];
+        c = min(c, at(y + 2, x + 1) + LONGW); c = min(c, at(y + 2, x - 1) + LONGW); c = min(c, at(y + 1, x + 2) + LONGW);
+        c = min(c, at(y + 1, x + 1) + DIAG); c = min(c, at(y + 1, x) + kChamHV); c = min(c, at(y + 1, x - 1) + DIAG);
+        c = min(c, at(y + 1, x - 2) + LONGW);
+        v = (int)c - j * (int)kChamHV;
+      }
+      const int pm = block_prefix_min(v, warp_sm, carry);
+      if (j < w) {
+        const unsigned d = (unsigned)(pm + j * (int)kChamHV);
+        T[(size_t)y * w + x] = d;
+        D[(size_t)y * w + x] = __fmul_rn(__uint2float_rn(min(d, DMAX)), scale);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// isStatic of every pair / triplet constraint: dist > distance at all ends; pixel = (int(loc.x * w), int(loc.y * w)) -- the reference
+// scales y by the mask WIDTH as well (:618-621).  items: [n][3] frames (-1 = unused end), locs: [total][2 * ends] float32.
+__global__ void __launch_bounds__(256) k_static_flags(const float* __restrict__ dist, int h, int w, float distance, int ends, const int* __restrict__ item_frames,
+                                                       const long long* __restrict__ offsets, int nitems, const float* __restrict__ locs, uint8_t* __restrict__ flags) {
+  const int item = blockIdx.y;
+  if (item >= nitems) return;
+  const long long b = offsets[item], n = offsets[item + 1] - b;
+  const size_t plane = (size_t)w * h;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float* L = locs + (size_t)(b + i) * 2 * ends;
+    bool st = true;
+    for (int e = 0; e < ends; ++e) {
+      const int f = item_frames[item * 3 + e];
+      int ix = (int)__fmul_rn(L[2 * e], (float)w), iy = (int)__fmul_rn(L[2 * e + 1], (float)w);
+      ix = min(max(ix, 0), w - 1); iy = min(max(iy, 0), h - 1);     // the reference indexes unchecked
+      st = st && (dist[(size_t)f * plane + (size_t)iy * w + ix] > distance);
+    }
+    flags[b + i] = st ? 1 : 0;
+  }
 }
 
 struct BuilderArgs {

@@ -134,24 +134,36 @@ __device__ __forceinline__ void tile_mma_nt(const double* __restrict__ At, const
 // against 5.6 k -- the F2F conversions cost more than the library's MUFU.RSQ64H path; a rotated-row loop form that is not
 // unrolled over j: 17 k cycles.)
 __device__ __forceinline__ void warp_chol16(double* __restrict__ D, double* __restrict__ pinv, int lane, int* __restrict__ fail) {
+  // Pivot-first ordering (round 2): the chain of a right-looking step is  l_{j+1,j} -> a_{j+1,j+1} -> rsqrt -> column scale; the
+  // column-(j+1) update and the next pivot's rsqrt are issued BEFORE the other 14 - j column updates of step j, which then fill
+  // the rsqrt latency instead of delaying it (measured: 5.6 k -> see DESIGN.md cycles per tile).
   const int i = lane & 15;
   double a[16];
 #pragma unroll
   for (int c = 0; c < 16; ++c) a[c] = (c <= i) ? D[swz(i, c)] : 0.0;
+  double d = __shfl_sync(0xffffffffu, a[0], 0);
+  if (!(d > 0.0) || !isfinite(d)) { if (lane == 0) *fail = 1; d = 1.0; }
+  double pi = rsqrt(d);
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    double d = __shfl_sync(0xffffffffu, a[j], j);
-    if (!(d > 0.0) || !isfinite(d)) { if (lane == 0) *fail = 1; d = 1.0; }
-    const double pi = rsqrt(d);
     const double lij = (i == j) ? d * pi : a[j] * pi;
     if (i >= j) a[j] = lij;
     if (lane == 0) pinv[j] = pi;
+    if (j < 15) {
+      // critical column first: a[:, j+1] -= l[:, j] l_{j+1,j}, then the next pivot and its reciprocal square root
+      const double l1 = __shfl_sync(0xffffffffu, lij, j + 1);
+      if (i >= j + 1) a[j + 1] -= lij * l1;
+      double dn = __shfl_sync(0xffffffffu, a[j + 1], j + 1);
+      if (!(dn > 0.0) || !isfinite(dn)) { if (lane == 0) *fail = 1; dn = 1.0; }
+      const double pin = rsqrt(dn);
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      if (c > j) {   // constant trip count so that a[] stays in registers
-        const double lcj = __shfl_sync(0xffffffffu, a[j], c);
-        if (i >= c) a[c] -= lij * lcj;
+      for (int c = 0; c < 16; ++c) {
+        if (c > j + 1) {   // constant trip count so that a[] stays in registers
+          const double lcj = __shfl_sync(0xffffffffu, lij, c);
+          if (i >= c) a[c] -= lij * lcj;
+        }
       }
+      d = dn; pi = pin;
     }
   }
   if (lane < 16) {

@@ -22,46 +22,55 @@ namespace rcvdh {
 static bool fileExists(const std::string& f) { struct stat st; return stat(f.c_str(), &st) == 0; }
 static std::string pairName(const char* fmt, const std::string& path, int a, int b) { char buf[512]; snprintf(buf, sizeof(buf), fmt, path.c_str(), a, b); return buf; }
 
-// cv::cvtColor(COLOR_BGR2GRAY) for CV_32FC3: b*0.114f + g*0.587f + r*0.299f (float arithmetic)
+// cv::cvtColor(COLOR_BGR2GRAY) for CV_32FC3 in the operation order of OpenCV 4.13's vector body (RGB2Gray<float>, found by search
+// against cv2, tests/test_host.py): fma(r, 0.299f, fma(b, 0.114f, g * 0.587f)).  Built with -ffp-contract=off: every fusion is explicit.
 Image bgr2gray32f(const Image& bgr) {
   if (bgr.type != cvMakeType(CV_32F, 3)) throw std::runtime_error("bgr2gray32f expects CV_32FC3.");
   Image g; g.create(bgr.rows, bgr.cols, cvMakeType(CV_32F, 1));
   const float* s = bgr.ptr<float>(); float* d = g.ptr<float>();
   const float cb = 0.114f, cg = 0.587f, cr = 0.299f;
-  for (size_t i = 0; i < size_t(bgr.rows) * bgr.cols; ++i) d[i] = s[3 * i] * cb + s[3 * i + 1] * cg + s[3 * i + 2] * cr;
+  for (size_t i = 0; i < size_t(bgr.rows) * bgr.cols; ++i) d[i] = std::fmaf(s[3 * i + 2], cr, std::fmaf(s[3 * i], cb, s[3 * i + 1] * cg));
   return g;
 }
 static inline int reflect101(int p, int n) { if (n == 1) return 0; while (p < 0 || p >= n) { if (p < 0) p = -p; else p = 2 * n - 2 - p; } return p; }
-// cv::cornerMinEigenVal(src, dst, blockSize = 3, ksize = 3, BORDER_DEFAULT) for CV_32FC1:
-// Sobel derivatives scaled by 1/(2^(ksize-1) * blockSize) = 1/12, covariance products, 3x3 box sum
-// (normalize = false), then (a + c) - sqrt((a - c)^2 + b^2) with a = dxx/2, b = dxy, c = dyy/2.
+// cv::cornerMinEigenVal(src, dst, blockSize = 3, ksize = 3, BORDER_DEFAULT) for CV_32FC1, bit-exact with cv2 4.13 (AVX2 paths):
+// Sobel with the scale 1/(2^(ksize-1) * blockSize) = 1/12 folded into the smoothing kernel (cv::Sobel), fused where OpenCV's
+// universal intrinsics fuse; covariance products; 3x3 box sum accumulated in double (cv::boxFilter, CV_64F sum type, normalize =
+// false) and rounded once; then (a + c) - sqrt((a - c)^2 + b^2) with a = dxx/2, b = dxy, c = dyy/2, unfused.
 Image cornerMinEigenVal3(const Image& src) {
   const int h = src.rows, w = src.cols;
-  const float scale = 1.f / 12.f;
+  const float scale = 1.f / 12.f, scale2 = 2.f * scale;
   std::vector<float> dx(size_t(w) * h), dy(size_t(w) * h);
   const float* S = src.ptr<float>();
   auto at = [&](int y, int x) { return S[size_t(reflect101(y, h)) * w + reflect101(x, w)]; };
-  // separable Sobel: row pass first, then column pass with the scaled smoothing / derivative kernel
-  std::vector<float> rd(size_t(w) * h), rs(size_t(w) * h);   // row derivative [-1 0 1], row smoothing [1 2 1]
+  std::vector<float> rd(size_t(w) * h), rs(size_t(w) * h);   // row derivative [-1 0 1] (unscaled), row smoothing [s 2s s]
+  const int wvec = w & ~3;                                    // SymmRowSmallVec_32f body; the scalar tail fuses the other way round
   for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) {
     const float a = at(y, x - 1), b = at(y, x), c = at(y, x + 1);
     rd[size_t(y) * w + x] = c - a;
-    rs[size_t(y) * w + x] = a + c + b * 2.f;   // only used unscaled; scale goes to the other kernel below
+    const float lr = a + c;
+    rs[size_t(y) * w + x] = x < wvec ? std::fmaf(b, scale2, lr * scale) : std::fmaf(lr, scale, b * scale2);
   }
   auto rdAt = [&](int y, int x) { return rd[size_t(reflect101(y, h)) * w + x]; };
   auto rsAt = [&](int y, int x) { return rs[size_t(reflect101(y, h)) * w + x]; };
   for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) {
-    // dx: kx = [-1 0 1] (rows), ky = [1 2 1] * scale (columns)
-    dx[size_t(y) * w + x] = (rdAt(y - 1, x) + rdAt(y + 1, x)) * scale + rdAt(y, x) * (2.f * scale);
-    // dy: kx = [1 2 1] * scale applied in the row pass in OpenCV; algebraically the same product
-    dy[size_t(y) * w + x] = (rsAt(y + 1, x) - rsAt(y - 1, x)) * scale;
+    dx[size_t(y) * w + x] = std::fmaf(rdAt(y - 1, x) + rdAt(y + 1, x), scale, rdAt(y, x) * scale2);   // column [s 2s s] (SymmColumnSmallVec_32f)
+    dy[size_t(y) * w + x] = rsAt(y + 1, x) - rsAt(y - 1, x);                                          // column [-1 0 1]
   }
   std::vector<float> cxx(size_t(w) * h), cxy(size_t(w) * h), cyy(size_t(w) * h);
   for (size_t i = 0; i < size_t(w) * h; ++i) { cxx[i] = dx[i] * dx[i]; cxy[i] = dx[i] * dy[i]; cyy[i] = dy[i] * dy[i]; }
   auto box = [&](const std::vector<float>& in, std::vector<float>& out) {
-    std::vector<float> tmp(size_t(w) * h);
-    for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) tmp[size_t(y) * w + x] = in[size_t(y) * w + reflect101(x - 1, w)] + in[size_t(y) * w + x] + in[size_t(y) * w + reflect101(x + 1, w)];
-    for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) out[size_t(y) * w + x] = tmp[size_t(reflect101(y - 1, h)) * w + x] + tmp[size_t(y) * w + x] + tmp[size_t(reflect101(y + 1, h)) * w + x];
+    std::vector<double> tmp(size_t(w) * h);
+    for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) tmp[size_t(y) * w + x] = (double(in[size_t(y) * w + reflect101(x - 1, w)]) + double(in[size_t(y) * w + x])) + double(in[size_t(y) * w + reflect101(x + 1, w)]);
+    // ColumnSum<double, float>: the running sum slides down the column (its last bit decides exact float ties, so the recurrence is kept)
+    for (int x = 0; x < w; ++x) {
+      double sum = tmp[size_t(reflect101(-1, h)) * w + x] + tmp[x];
+      for (int y = 0; y < h; ++y) {
+        const double s0 = sum + tmp[size_t(reflect101(y + 1, h)) * w + x];
+        out[size_t(y) * w + x] = float(s0);
+        sum = s0 - tmp[size_t(reflect101(y - 1, h)) * w + x];
+      }
+    }
   };
   std::vector<float> bxx(size_t(w) * h), bxy(size_t(w) * h), byy(size_t(w) * h);
   box(cxx, bxx); box(cxy, bxy); box(cyy, byy);
@@ -378,7 +387,7 @@ void FlowConstraintsCollection::computeOnDevice() {
     std::vector<float> pout, tout;
     for (int attempt = 0; attempt < 2; ++attempt) {
       pout.resize(size_t(pcap) * 4); tout.resize(size_t(tcap) * 6);
-      const int rc = rcvd_build_constraints(&prm, 0, color.data(), hasDyn ? dyn.data() : nullptr, pf.data(), pflow.data(), pmask.data(), tf.data(), tflow.data(), tmask.data(),
+      const int rc = rcvd_build_constraints(&prm, currentDevice(), color.data(), hasDyn ? dyn.data() : nullptr, pf.data(), pflow.data(), pmask.data(), tf.data(), tflow.data(), tmask.data(),
                                             poff.data(), pout.data(), pcap, toff.data(), tout.data(), tcap);
       if (rc == RCVD_OK) break;
       if (attempt == 0 && (poff[np] > pcap || toff[nt] > tcap)) { pcap = poff[np]; tcap = toff[nt]; continue; }   // sizes are known now
@@ -394,7 +403,7 @@ void FlowConstraintsCollection::computeOnDevice() {
     }
     pi += np; ti += nt;
   }
-  rcvd_trim_device_memory(0);
+  rcvd_trim_device_memory(currentDevice());
 }
 
 void FlowConstraintsCollection::resetStaticFlag() {
@@ -406,6 +415,36 @@ void FlowConstraintsCollection::setStaticFlagFromDynamicMask(int distance) {   /
   logInfo("Setting static flag from dynamic masks...");
   ColorStream& ms = video_->colorStream("dynamic_mask");
   const int w = ms.width(), h = ms.height();
+  {
+    // default: distance transforms + per-constraint lookups on the device (rcvd_static_flags); RCVD_CONSTRAINT_BUILDER=host
+    // selects the sequential restatement below (no automatic fallback)
+    const char* sel = std::getenv("RCVD_CONSTRAINT_BUILDER");
+    if (sel && !(std::string(sel) == "host" || std::string(sel) == "gpu" || std::string(sel).empty())) throw std::runtime_error("RCVD_CONSTRAINT_BUILDER must be 'gpu' or 'host'.");
+    if (!sel || std::string(sel) != "host") {
+      const int F = video_->numFrames(); const size_t plane = size_t(w) * h;
+      std::vector<uint8_t> masks(size_t(F) * plane, 255);
+      std::vector<uint8_t> used(F, 0);
+      for (auto& kv : pairs_) { used[kv.first.first] = 1; used[kv.first.second] = 1; }
+      for (auto& kv : triplets_) { used[kv.first - 1] = 1; used[kv.first] = 1; used[kv.first + 1] = 1; }
+      for (int f = 0; f < F; ++f) {
+        if (!used[f]) continue;
+        const Image* m = ms.frame(f).image();
+        if (!m) throw std::runtime_error("Dynamic mask stream is missing a frame.");
+        if (m->cols != w || m->rows != h) throw std::runtime_error("Dynamic masks have inconsistent dimensions.");
+        std::memcpy(masks.data() + size_t(f) * plane, m->data.data(), plane);
+      }
+      std::vector<int32_t> pf, tf; std::vector<int64_t> po(1, 0), to(1, 0); std::vector<float> pl, tl;
+      for (auto& kv : pairs_) { pf.push_back(kv.first.first); pf.push_back(kv.first.second); for (auto& c : kv.second) pl.insert(pl.end(), &c.loc[0][0], &c.loc[0][0] + 4); po.push_back(po.back() + int64_t(kv.second.size())); }
+      for (auto& kv : triplets_) { tf.push_back(kv.first); for (auto& c : kv.second) tl.insert(tl.end(), &c.loc[0][0], &c.loc[0][0] + 6); to.push_back(to.back() + int64_t(kv.second.size())); }
+      std::vector<uint8_t> ps(size_t(po.back()) + 1), ts(size_t(to.back()) + 1);
+      const int rc = rcvd_static_flags(currentDevice(), masks.data(), F, h, w, float(distance), int(pf.size() / 2), pf.data(), po.data(), pl.data(), ps.data(),
+                                       int(tf.size()), tf.data(), to.data(), tl.data(), ts.data(), nullptr);
+      if (rc != RCVD_OK) throw std::runtime_error(std::string("rcvd_static_flags failed: ") + rcvd_last_error());
+      size_t i = 0; for (auto& kv : pairs_) for (auto& c : kv.second) c.isStatic = ps[i++] != 0;
+      i = 0; for (auto& kv : triplets_) for (auto& c : kv.second) c.isStatic = ts[i++] != 0;
+      return;
+    }
+  }
   std::vector<Image> masks(video_->numFrames());
   auto getMask = [&](int f) -> const Image& {
     if (masks[f].empty()) { Image dd = dynamicDistance(f); masks[f].create(dd.rows, dd.cols, cvMakeType(CV_8U, 1));

@@ -264,20 +264,20 @@ Image Xform::paramMap(const DepthFrame& df) const {
   rcvd_config cfg; denseConfig(desc_, cfg);
   const int w = df.width(), h = df.height();
   Image out; out.create(h, w, cvMakeType(CV_64F, valueParams()));
-  if (rcvd_depth_param_map(&cfg, 0, params_.data(), out.ptr<double>(), h, w) != RCVD_OK) throw std::runtime_error(rcvd_last_error());
+  if (rcvd_depth_param_map(&cfg, currentDevice(), params_.data(), out.ptr<double>(), h, w) != RCVD_OK) throw std::runtime_error(rcvd_last_error());
   return out;
 }
 Image Xform::warp(int h, int w) const {
   if (desc_.type != XformType::Spatial) throw std::runtime_error("Transform has the wrong type.");
   rcvd_config cfg; denseConfig(desc_, cfg);
   Image out; out.create(h, w, cvMakeType(CV_32F, 2));
-  if (rcvd_spatial_warp(&cfg, 0, params_.data(), out.ptr<float>(), h, w) != RCVD_OK) throw std::runtime_error(rcvd_last_error());
+  if (rcvd_spatial_warp(&cfg, currentDevice(), params_.data(), out.ptr<float>(), h, w) != RCVD_OK) throw std::runtime_error(rcvd_last_error());
   return out;
 }
 Image Xform::apply(const Image& src) const {
   rcvd_config cfg; denseConfig(desc_, cfg);
   Image out; out.create(src.rows, src.cols, cvMakeType(CV_32F, 1));
-  if (rcvd_depth_apply(&cfg, 0, params_.data(), src.ptr<float>(), out.ptr<float>(), src.rows, src.cols) != RCVD_OK) throw std::runtime_error(rcvd_last_error());
+  if (rcvd_depth_apply(&cfg, currentDevice(), params_.data(), src.ptr<float>(), out.ptr<float>(), src.rows, src.cols) != RCVD_OK) throw std::runtime_error(rcvd_last_error());
   return out;
 }
 

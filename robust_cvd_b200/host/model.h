@@ -19,6 +19,12 @@
 #include "../../include/rcvd.h"
 
 namespace rcvdh {
+// CUDA device of every device call of the host layer: the caller's current device (or RCVD_DEVICE); 0 when no device is usable so that
+// the entry point itself reports RCVD_ERR_NO_DEVICE.
+inline int currentDevice() { const int d = rcvd_current_device(); return d < 0 ? 0 : d; }
+}
+
+namespace rcvdh {
 
 // OpenCV type codes used on the Python side (cv2.CV_8UC1 ...): depth + ((cn-1) << 3)
 constexpr int CV_8U = 0, CV_32S = 4, CV_32F = 5, CV_64F = 6;

@@ -172,7 +172,7 @@ DepthVideoPoseOptimizer::ProblemArrays DepthVideoPoseOptimizer::buildProblem(con
 void DepthVideoPoseOptimizer::solveAndWriteBack(ProblemArrays& pa, const Params& params, bool writePoses) {
   logInfo("Solving...");
   rcvd_problem* p = nullptr;
-  checkStatus(rcvd_problem_create(&pa.cfg, 0, &p));
+  checkStatus(rcvd_problem_create(&pa.cfg, currentDevice(), &p));
   try {
     checkStatus(rcvd_problem_set_frames(p, pa.inRange.data(), pa.median.data(), pa.adaptive.empty() ? nullptr : pa.adaptive.data()));
     checkStatus(rcvd_problem_set_constraints(p, int(pa.pairFrames.size() / 2), pa.pairFrames.data(), pa.offsets.data(), pa.records.data()));
@@ -275,7 +275,7 @@ void DepthVideoPoseOptimizer::poseOptimization(const Params& params, const FlowC
 
 // ---------------------------------------------------------------------------
 void DepthVideoProcessor::process(const Params& params) {   // lib/Processor.cpp:115-144
-  struct Trim { ~Trim() { rcvd_trim_device_memory(0); } } trimAtExit;   // hand the cached device memory back (PyTorch shares the GPU)
+  struct Trim { ~Trim() { rcvd_trim_device_memory(currentDevice()); } } trimAtExit;   // hand the cached device memory back (PyTorch shares the GPU)
   switch (params.op) {
     case Op::None: break;
     case Op::GridXformSplit: gridXformSplit(params); break;
@@ -393,7 +393,7 @@ void DepthVideoProcessor::flowGuidedFilter(const Params& params) {
   prm.frame_radius = params.frameRadius; prm.spatial_radius = params.spatialRadius; prm.median = params.median ? 1 : 0; prm.num_far = int(farPairs.size() / 2);
   prm.inv_aspect = video_->invAspect();
   std::vector<float> out(size_t(prm.num_out) * plane);
-  const int rc = rcvd_flow_guided_filter(&prm, 0, depth.data(), cams.data(), fwd.empty() ? nullptr : fwd.data(), fwdMask.empty() ? nullptr : fwdMask.data(),
+  const int rc = rcvd_flow_guided_filter(&prm, currentDevice(), depth.data(), cams.data(), fwd.empty() ? nullptr : fwd.data(), fwdMask.empty() ? nullptr : fwdMask.data(),
                                          bwd.empty() ? nullptr : bwd.data(), bwdMask.empty() ? nullptr : bwdMask.data(),
                                          farPairs.empty() ? nullptr : farPairs.data(), farFlow.empty() ? nullptr : farFlow.data(), farMask.empty() ? nullptr : farMask.data(), out.data());
   if (rc != RCVD_OK) throw std::runtime_error(std::string("flow guided filter failed: ") + rcvd_last_error());
@@ -448,11 +448,11 @@ void DepthVideoProcessor::resetDepthXforms(const Params& params) { video_->depth
 void DepthVideoProcessor::resetSpatialXforms(const Params& params) { video_->depthStream(params.depthStream).resetSpatialXforms(params.spatialXformDesc); }
 void DepthVideoProcessor::normalizeDepth(const Params& params, const FlowConstraintsCollection& constraints) {
   DepthVideoPoseOptimizer optimizer(video_, params.depthStream); optimizer.normalizeDepth(params.poseOptimizer, constraints);
-  rcvd_trim_device_memory(0);
+  rcvd_trim_device_memory(currentDevice());
 }
 void DepthVideoProcessor::optimizePoses(const Params& params, const FlowConstraintsCollection& constraints) {
   DepthVideoPoseOptimizer optimizer(video_, params.depthStream); optimizer.poseOptimization(params.poseOptimizer, constraints);
-  rcvd_trim_device_memory(0);   // the solver's cached device memory goes back to the driver: the fine-tuning stage (PyTorch) runs next on this GPU
+  rcvd_trim_device_memory(currentDevice());   // the solver's cached device memory goes back to the driver: the fine-tuning stage (PyTorch) runs next on this GPU
 }
 
 }  // namespace rcvdh

@@ -176,6 +176,10 @@ class Problem:
         """Test hook: False forces the generic accumulate kernel."""
         _check(self.L.rcvd_debug_set_fast_path(self.h, C.c_int32(1 if on else 0)))
 
+    def set_update_kernel(self, tma=True, side_items_per_cta=0):
+        """Test / bench hook: persistent TMA-fed update kernel (default) or the round-1 cp.async kernel."""
+        _check(self.L.rcvd_debug_set_update_kernel(self.h, C.c_int32(1 if tma else 0), C.c_int32(side_items_per_cta)))
+
     def set_side_slice(self, ctas):
         _check(self.L.rcvd_debug_set_side_slice(self.h, C.c_int32(ctas)))
 
@@ -277,6 +281,25 @@ def build_constraints(color_bgr, pair_frames, pair_flow, pair_mask, match_separa
             continue
         _check(rc)
     return poff, pout[:poff[P]], toff, tout[:toff[T]]
+
+
+def static_flags(masks, distance, pair_frames=None, pair_offsets=None, pair_locs=None, trip_frames=None, trip_offsets=None, trip_locs=None, want_distance=False, device=0):
+    """rcvd_static_flags (FlowConstraintsCollection::setStaticFlagFromDynamicMask + dynamicDistance, reference lib/FlowConstraints.cpp:573-660,
+    :257-286) on the GPU.  masks [F,h,w] u8.  Returns (pair_static u8[n], trip_static u8[m], distance images [F,h,w] f32 or None)."""
+    m = np.ascontiguousarray(masks, np.uint8); F, h, w = m.shape
+    P = 0 if pair_frames is None else len(pair_frames); T = 0 if trip_frames is None else len(trip_frames)
+    pf = np.ascontiguousarray(pair_frames, np.int32).reshape(-1, 2) if P else None
+    po = np.ascontiguousarray(pair_offsets, np.int64) if P else None
+    pl = np.ascontiguousarray(pair_locs, np.float32).reshape(-1, 4) if P else None
+    tf = np.ascontiguousarray(trip_frames, np.int32) if T else None
+    to = np.ascontiguousarray(trip_offsets, np.int64) if T else None
+    tl = np.ascontiguousarray(trip_locs, np.float32).reshape(-1, 6) if T else None
+    ps = np.zeros(int(po[-1]) if P else 0, np.uint8); ts = np.zeros(int(to[-1]) if T else 0, np.uint8)
+    dist = np.zeros((F, h, w), np.float32) if want_distance else None
+    _check(lib().rcvd_static_flags(C.c_int32(device), _p(m, C.c_uint8), C.c_int32(F), C.c_int32(h), C.c_int32(w), C.c_float(distance),
+                                   C.c_int32(P), _p(pf, C.c_int32), _p(po, C.c_int64), _p(pl, C.c_float), _p(ps if P else None, C.c_uint8),
+                                   C.c_int32(T), _p(tf, C.c_int32), _p(to, C.c_int64), _p(tl, C.c_float), _p(ts if T else None, C.c_uint8), _p(dist, C.c_float)))
+    return ps, ts, dist
 
 
 def fp64_tensor_peak(device=0):

@@ -44,7 +44,10 @@ def rodrigues(w):
 
 class Scene:
     def __init__(self, num_frames, width, height, seed=0, motion=0.02, rot_deg=0.3,
-                 scale_sigma=0.15, depth_noise=0.01, flow_noise=0.1, focal_long=0.3461538376301239):
+                 scale_sigma=0.15, depth_noise=0.01, flow_noise=0.1, focal_long=0.3461538376301239,
+                 dolly=0.0, hole_fraction=0.0):
+        """dolly: constant speed along the initial viewing direction (-z), scene units per frame -- a divergent (expanding)
+        flow field; hole_fraction: fraction of every frame covered by seeded elliptic occluders (dynamic-mask holes)."""
         rng = np.random.default_rng(seed)
         self.N, self.w, self.h = num_frames, width, height
         self.aspect32 = np.float32(width) / np.float32(height)   # lib/DepthVideo.cpp:113
@@ -55,6 +58,9 @@ class Scene:
         # smooth random walk of the camera
         vel = np.cumsum(rng.normal(0, motion * 0.3, (num_frames, 3)), axis=0) * 0.2 + rng.normal(0, motion, (num_frames, 3))
         self.t = np.cumsum(vel, axis=0); self.t -= self.t[0]
+        if dolly:
+            self.t[:, 2] -= dolly * np.arange(num_frames)
+        self.hole_fraction = float(hole_fraction)
         wv = np.cumsum(rng.normal(0, np.deg2rad(rot_deg), (num_frames, 3)), axis=0)
         self.w_aa = wv - wv[0]
         self.R = np.stack([rodrigues(v) for v in self.w_aa])
@@ -125,6 +131,52 @@ class Scene:
         ok = depth > 1e-3
         return fx1.astype(np.float32), fy1.astype(np.float32), ok
 
+    # --- dynamic-mask holes (config 5) ---------------------------------------
+    def holes(self, f):
+        """Seeded elliptic occluders of frame f as rows (cx, cy, ax, ay) in pixels; their union covers ~hole_fraction of the
+        image (emulates dynamic-object masks: constraints starting or ending inside are dropped)."""
+        if self.hole_fraction <= 0:
+            return np.zeros((0, 4))
+        rng = np.random.default_rng(self.seed * 7919 + 31 * f + 5)
+        n = 6
+        area = -np.log(1.0 - min(self.hole_fraction, 0.95)) * self.w * self.h / n      # Poisson coverage: 1 - exp(-n a / A)
+        ax = np.sqrt(area / np.pi) * rng.uniform(0.7, 1.4, n); ay = area / (np.pi * ax)
+        return np.stack([rng.uniform(0, self.w, n), rng.uniform(0, self.h, n), ax, ay], axis=1)
+
+    def visible(self, f, px, py):
+        """False where pixel (px, py) of frame f lies inside one of its holes."""
+        ok = np.ones(np.shape(px), bool)
+        for cx, cy, ax, ay in self.holes(f):
+            ok &= ((px - cx) / ax) ** 2 + ((py - cy) / ay) ** 2 > 1.0
+        return ok
+
+    def mask_ratio(self, a, b, stride=8):
+        """Emulated flow-mask ratio of the pair (flow.py:49-66): share of (lattice) pixels of a whose flow target is a visible
+        pixel of b, minimum over the two directions -- the score column of flow_list.json."""
+        out = 1.0
+        py, px = np.mgrid[0:self.h:stride, 0:self.w:stride]
+        px = px.ravel(); py = py.ravel()
+        for s, d in ((a, b), (b, a)):
+            fx, fy, ok = self.flow(s, d, px, py)
+            ix = (fx + np.float32(0.5)).astype(np.int64); iy = (fy + np.float32(0.5)).astype(np.int64)
+            ok = ok & (fx >= 0) & (fy >= 0) & (ix < self.w) & (iy < self.h) & self.visible(s, px, py)
+            ok[ok] &= self.visible(d, ix[ok], iy[ok])
+            out = min(out, float(np.mean(ok)))
+        return out
+
+    def filtered_pairs(self, min_mask_ratio, pairs=None):
+        """Pairs kept by the dataset's overlap filter `score > min_mask_ratio` (loaders/video_dataset.py:129-136)."""
+        pairs = hierarchical2_pairs(self.N) if pairs is None else pairs
+        score = {}
+        keep = []
+        for (a, b) in pairs:
+            k = (min(a, b), max(a, b))
+            if k not in score:
+                score[k] = self.mask_ratio(*k)
+            if score[k] > min_mask_ratio:
+                keep.append((a, b))
+        return keep
+
     # --- constraint records -----------------------------------------------
     def pair_records(self, a, b, sep, rng, valid_fraction=1.0):
         """Records of directed pair a->b, emulating the greedy disc sampler's density
@@ -147,6 +199,9 @@ class Scene:
         fx1, fy1, ok = self.flow(a, b, ix, iy, rng)
         ix1 = (fx1 + np.float32(0.5)).astype(np.int32); iy1 = (fy1 + np.float32(0.5)).astype(np.int32)   # C (int) truncation
         ok &= (ix1 >= 0) & (ix1 < w) & (iy1 >= 0) & (iy1 < h) & (fx1 >= 0) & (fy1 >= 0)
+        if self.hole_fraction > 0:
+            ok &= self.visible(a, ix, iy)
+            ok[ok] &= self.visible(b, ix1[ok], iy1[ok])
         ix, iy, fx1, fy1 = ix[ok], iy[ok], fx1[ok], fy1[ok]
         sx = np.float32(1.0) / np.float32(w); sy = self.inv_aspect32 / np.float32(h)
         loc0x = ix.astype(np.float32) * sx; loc0y = iy.astype(np.float32) * sy

@@ -45,10 +45,9 @@ def test_builder_matches_numpy_cv2_restatement(tmp_path, sep):
     assert poff[0] == 0 and poff[-1] == len(pc) and len(tc) == 0
     import lib_python as lp
     for k, (a, b) in enumerate(sel):
-        # separation 10: priorities from the real cv2.cornerMinEigenVal; smaller separations keep thousands of near-equal
-        # priorities, so the sampler restatement is driven by the C++ operator restatement the CUDA kernels must match bit for bit
-        score = None if sep == 10 else np.asarray(lp._cornerMinEigenVal3(color[a]))
-        want, _ = host_ref.pair_constraints(color[a], flow[k], mask[k], sep, sc.inv_aspect32, score=score)
+        # priorities of the restatement come from the real cv2.cornerMinEigenVal at every separation (0 = every candidate survives,
+        # 1 / 3 keep thousands of near-equal priorities): the CUDA corner score is bit-equal to OpenCV's
+        want, _ = host_ref.pair_constraints(color[a], flow[k], mask[k], sep, sc.inv_aspect32)
         got = pc[poff[k]:poff[k + 1]]
         assert got.shape == want.shape, (k, got.shape, want.shape)
         np.testing.assert_array_equal(got, want)
@@ -85,6 +84,50 @@ def test_gpu_builder_equals_host_builder_through_lib_python(tmp_path, monkeypatc
         np.testing.assert_array_equal(gp[k], hp[k], err_msg=f"pair {k}")
     for k in gt:
         np.testing.assert_array_equal(gt[k], ht[k], err_msg=f"triplet {k}")
+
+
+def test_device_distance_transform_and_static_flags_match_host(tmp_path, monkeypatch):
+    """A2 on the device (rcvd_static_flags): the 5x5 fixed-point chamfer distance of every dynamic mask is bit-equal to the host restatement
+    of cv::distanceTransform(DIST_L2, 5) (and within the fixed-point/IPP float difference of the real cv2), and the static flags of all pair
+    and triplet constraints equal the sequential host pass through lib_python (reference lib/FlowConstraints.cpp:573-660)."""
+    import cv2
+    import lib_python as lp
+    sc, root, pairs = _scene(tmp_path, dynamic=True)
+    N, W, H = sc.N, sc.w, sc.h
+    masks = np.stack([cv2.imread(os.path.join(root, "dynamic_mask", f"frame_{i:06d}.png"), cv2.IMREAD_GRAYSCALE) for i in range(N)])
+    rng = np.random.default_rng(9)
+    stress = (rng.uniform(size=(3, 200, 333)) > 0.02).astype(np.uint8) * 255            # scattered single dynamic pixels, width not a multiple of the scan chunk
+    wide = np.full((1, 40, 700), 255, np.uint8); wide[0, 20, 5] = 0; wide[0, 3, 690] = 0  # distances that travel through several 256-column scan chunks
+    for mm in (masks, stress, wide):
+        l0 = solver.lib().rcvd_static_flag_launch_count()
+        _, _, dist = solver.static_flags(mm, 8.0, want_distance=True)
+        assert solver.lib().rcvd_static_flag_launch_count() > l0
+        for f in range(mm.shape[0]):
+            b = np.where(mm[f] < 127, 0, 255).astype(np.uint8)
+            np.testing.assert_array_equal(dist[f], np.asarray(lp._distanceTransformL2_5(b)))
+            np.testing.assert_allclose(dist[f], cv2.distanceTransform(b, cv2.DIST_L2, 5), rtol=1e-5, atol=1e-3)
+
+    def run(which):
+        monkeypatch.setenv("RCVD_CONSTRAINT_BUILDER", which)
+        v = lp.DepthVideo(); lp.DepthVideoImporter.importVideo(v, root, False)
+        v.createColorStream("down", "color_down", ".raw", CV_32FC3); v.createColorStream("dynamic_mask", "dynamic_mask", ".png", CV_8UC1)
+        v.createDepthStream("depth_midas2", "depth_midas2", [-1, -1])
+        fp = lp.FlowConstraintsParams(); fp.frameRange.resolve(v.numFrames(), True); fp.doNotUseCache = True
+        fc = lp.FlowConstraintsCollection(v, fp)
+        fc.setStaticFlagFromDynamicMask(8)
+        return {k: np.asarray(v_[1]) for k, v_ in fc._pairs().items()}, {k: np.asarray(v_[1]) for k, v_ in fc._triplets().items()}
+    l0 = solver.lib().rcvd_static_flag_launch_count()
+    gp, gt = run("gpu")
+    assert solver.lib().rcvd_static_flag_launch_count() > l0
+    l1 = solver.lib().rcvd_static_flag_launch_count()
+    hp, ht = run("host")
+    assert solver.lib().rcvd_static_flag_launch_count() == l1
+    n_dyn = 0
+    for k in gp:
+        np.testing.assert_array_equal(gp[k], hp[k], err_msg=f"pair {k}"); n_dyn += int((~gp[k].astype(bool)).sum())
+    for k in gt:
+        np.testing.assert_array_equal(gt[k], ht[k], err_msg=f"triplet {k}")
+    assert n_dyn > 0 and len(gp) == len(pairs)
 
 
 def test_builder_against_committed_golden():

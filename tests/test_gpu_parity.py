@@ -75,6 +75,36 @@ def test_lm_solve_matches_oracle(name, overrides):
     assert rel < 1e-4, rel
 
 
+@pytest.mark.parametrize("cubic", [0, 1])
+def test_adaptive_deformation_cost_with_node_weights(cubic):
+    """AdaptiveDeformationCost (reference lib/PoseOptimizer.cpp:559-656, :1470-1481) with non-zero per-node weights: residual of a grid
+    edge x (base + max(w_i, w_j) adaptive).  CUDA regulariser kernel vs the oracle: cost, gradient, normal matrix, LM trajectory."""
+    from oracle import oracle
+    from robust_cvd_b200 import solver
+    ov = dict(depth_type=abi.DEPTH_GRID, depth_grid_x=6, depth_grid_y=4, depth_cubic=cubic, depth_deform_reg=0.07, adaptive_deform=3.0)
+    sc, cfg, pairs, offs, rec, med = helpers.make_case(num_frames=8, **ov)
+    off_d, nd = helpers.layout_numbers(cfg)
+    rng = np.random.default_rng(21)
+    aw = rng.uniform(0.0, 1.0, (8, 4, 6)); aw[rng.uniform(size=aw.shape) < 0.4] = 0.0          # static regions have weight 0
+    O = oracle.OracleProblem(cfg); G = solver.Problem(cfg)
+    x = helpers.initial_state(sc, cfg, G.stride, off_d, nd, perturb=0.03)
+    helpers.setup_problem(O, cfg, pairs, offs, rec, med, x, adaptive=aw)
+    helpers.setup_problem(G, cfg, pairs, offs, rec, med, x, adaptive=aw)
+    co, go = O.evaluate(True); cg, gg = G.evaluate(True)
+    assert abs(co - cg) <= 1e-11 * abs(co) and np.abs(go - gg).max() <= 1e-9 * max(1.0, np.abs(go).max())
+    Ho, Hg = O.normal_matrix_dense(), G.normal_matrix_dense()
+    assert np.abs(Ho - Hg).max() <= 1e-9 * np.abs(Ho).max()
+    # the weights matter: the same problem without them has a different cost
+    cfg0 = abi.default_config(8, sc.aspect, **dict(ov, adaptive_deform=0.0))
+    G0 = solver.Problem(cfg0); helpers.setup_problem(G0, cfg0, pairs, offs, rec, med, x)
+    assert abs(G0.evaluate() - cg) > 1e-6 * abs(cg)
+    opt = abi.default_solve_options(max_iterations=40)
+    so, sg = O.solve(opt), G.solve(opt)
+    assert so.termination == sg.termination and abs(so.iterations - sg.iterations) <= 2
+    assert abs(so.final_cost - sg.final_cost) <= 1e-6 * abs(so.final_cost)
+    assert np.linalg.norm(O.get_state() - G.get_state()) <= 1e-4 * np.linalg.norm(O.get_state())
+
+
 @pytest.mark.parametrize("name", ["bilinear_perframe_disp", "global_perframe_disp", "bilinear_fixedintr_ratio", "global_euclid", "identitydepth_perframe"])
 def test_fast_kernel_matches_generic(name):
     overrides = dict(helpers.VARIANTS)[name]

@@ -58,6 +58,7 @@ def _check_case(name, frames, lm_iters=4):
     rng = np.random.default_rng(3)
     U = cfg.num_frames * G.stride
     S = 1.0 / (1.0 + rng.uniform(0.5, 50.0, U)); D2 = rng.uniform(1e-4, 1e-2, U); b = rng.normal(0, 1, U)
+    O.time_iteration()                # assembles the oracle's H at the current state (block_solve factors the last assembled H)
     yg = G.debug_linear_solve(S, D2, b); yo = O.block_solve(S, D2, b)
     assert np.linalg.norm(yg - yo) <= 1e-9 * np.linalg.norm(yo), np.linalg.norm(yg - yo) / np.linalg.norm(yo)
     # a few LM iterations

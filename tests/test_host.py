@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "robust_cvd_b200", "host"))
 
 lp = pytest.importorskip("lib_python")
-from robust_cvd_b200 import synthetic, synthetic_files  # noqa: E402
+from robust_cvd_b200 import abi, synthetic, synthetic_files  # noqa: E402
 from oracle import host_ref  # noqa: E402
 
 CV_32FC3, CV_8UC1 = 21, 0
@@ -194,7 +194,13 @@ def test_image_operators_against_cv2(scene_dir):
     color = synthetic_files.read_raw(f"{root}/color_down/frame_000003.raw")
     ref = cv2.cornerMinEigenVal(cv2.cvtColor(color, cv2.COLOR_BGR2GRAY), 3)
     mine = lp._cornerMinEigenVal3(color)
-    assert np.abs(mine - ref).max() <= 2e-6 * ref.max()        # same formula; OpenCV's SIMD/FMA order differs in the last bits
+    np.testing.assert_array_equal(np.asarray(mine), ref)        # bit-exact: OpenCV's fused / double-accumulated operation order restated
+    # ... at the BASELINE image sizes and at a width that exercises OpenCV's scalar tail (w % 4 != 0)
+    rng = np.random.default_rng(11)
+    for (hh, ww) in ((224, 384), (384, 640), (37, 53)):
+        img = rng.uniform(0, 1, (hh, ww, 3)).astype(np.float32)
+        img = (cv2.GaussianBlur(img, (0, 0), 1.5) + 0.2 * rng.uniform(0, 1, (hh, ww, 3)).astype(np.float32)).astype(np.float32)
+        np.testing.assert_array_equal(np.asarray(lp._cornerMinEigenVal3(img)), cv2.cornerMinEigenVal(cv2.cvtColor(img, cv2.COLOR_BGR2GRAY), 3))
     b = np.where(masks[1] < 127, 0, 255).astype(np.uint8)
     # OpenCV's own fixed-point 5x5 chamfer vs the IPP float variant that pip-built cv2 dispatches to: metric 1.4 is
     # 91750/65536 in the former, float(1.4) in the latter -> differences of a few 1e-6 per step, irrelevant for the '> 8' test
@@ -232,6 +238,38 @@ def test_problem_assembly_records(scene_dir):
     d2 = opt._buildProblem(params, fc, 0.1, False)
     assert set(map(tuple, d2["pair_frames"].reshape(-1, 2))) == {k for k in fc._pairs() if k[0] <= 3 and k[1] <= 3}
     assert d2["in_range"].tolist() == [1, 1, 1, 1, 0, 0, 0, 0]
+
+
+def test_adaptive_deformation_node_weights_follow_reference_splat(scene_dir):
+    """AdaptiveDeformationCost constructor (reference lib/PoseOptimizer.cpp:559-619): every dynamic-mask pixel is splatted bilinearly onto
+    the depth grid into a static or a dynamic accumulator; node weight = dynamic / (dynamic + static).  Restated here in numpy."""
+    sc, root, pairs, masks = scene_dir
+    v = _open(root)
+    fp = lp.FlowConstraintsParams(); fp.frameRange.resolve(v.numFrames(), True)
+    fc = lp.FlowConstraintsCollection(v, fp)
+    proc = lp.DepthVideoProcessor(v)
+    pp = lp.DepthVideoProcessor.Params(); pp.depthStream = v.numDepthStreams() - 1
+    pp.depthXformDesc.type = lp.XformType.Depth; pp.depthXformDesc.parse("Grid(Scale, Linear, 6, 4, 1)")
+    pp.op = lp.DepthVideoProcessor.Op.ResetDepthXforms; proc.process(pp)
+    opt = lp.DepthVideoPoseOptimizer(v, pp.depthStream)
+    params = lp.DepthVideoPoseOptimizer.Params(); params.frameRange.fromString("0-7"); params.adaptiveDeformationCost = 2.5
+    d = opt._buildProblem(params, fc, 0.1, False)
+    gw, gh = 6, 4
+    got = d["adaptive"].reshape(8, gh, gw)
+    for f in range(8):
+        m = masks[f]; dh, dw = m.shape
+        dyn = np.zeros((gh, gw)); sta = np.zeros((gh, gw))
+        fy = np.arange(dh, dtype=np.float64) * (gh - 1) / dh; iy = fy.astype(int); ry = fy - iy
+        fx = np.arange(dw, dtype=np.float64) * (gw - 1) / dw; ix = fx.astype(int); rx = fx - ix
+        for y in range(dh):          # same accumulation order as the reference loop (row-major), so the sums agree to the last bit
+            for x in range(dw):
+                w = sta if m[y, x] > 127 else dyn
+                w[iy[y], ix[x]] += (1.0 - rx[x]) * (1.0 - ry[y]); w[iy[y], ix[x] + 1] += rx[x] * (1.0 - ry[y])
+                w[iy[y] + 1, ix[x]] += (1.0 - rx[x]) * ry[y]; w[iy[y] + 1, ix[x] + 1] += rx[x] * ry[y]
+        np.testing.assert_array_equal(got[f], dyn / (dyn + sta))
+    assert got.max() > 0.05 and got.min() == 0.0            # the blobs really reach some nodes
+    cfg = abi.Config.from_buffer_copy(d["config"])
+    assert cfg.adaptive_deform == 2.5 and cfg.depth_deform_reg == 0.1
 
 
 def test_descriptor_strings_and_frame_range():
