@@ -208,7 +208,10 @@ def run_ours(args):
     P.set_state(x0)
     if args.legacy_update or args.side_ipc:
         P.set_update_kernel(not args.legacy_update, args.side_ipc)
+    if world > 1 and args.no_dist:
+        P.set_distributed(False)
     info = P.structure_info()
+    dinfo = P.distribution_info()
 
     def sync_all():
         if world > 1:
@@ -327,7 +330,8 @@ def run_ours(args):
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload if not args.frames else f"{args.workload}[frames={args.frames}]", "frames": spec["frames"], "image": [spec["w"], spec["h"]],
                        "depth_grid": [spec["gx"], spec["gy"]], "match_separation": spec["sep"], "pairs": int(len(pairs)), "constraints": C_total,
-                       "unknowns": int(cfg.num_frames * nf), "parallelism": f"pair-sharded x{world}, replicated solve", "l2_note": "H/L working set >> L2 (126 MB)",
+                       "unknowns": int(cfg.num_frames * nf), "parallelism": (f"pair-sharded x{world}; " + ("H reduced to block owners, wide elimination levels factored by frame owners (one fused NCCL broadcast of the new factor blocks per level), narrow tail + substitution replicated" if dinfo["distributed"] else "H all-reduced, factorisation replicated")) if world > 1 else "single GPU",
+                       "distribution": dinfo, "l2_note": "H/L working set >> L2 (126 MB)",
                        "structure": info},
             "breakdown_ms": {"accumulate": tm["accumulate_ms"], "factor_solve": tm["linear_ms"], "candidate_cost": tm["cost_ms"], "accumulate_isolated": acc_ms},
             "linear_kernels_ms_serialised": {k: lin_prof[k] for k in ("load_ms", "potrf_ms", "trinv_ms", "trsm_ms", "gemm_ms", "solve_ms")},
@@ -339,6 +343,15 @@ def run_ours(args):
             line["cpu_baseline"] = {k: v for k, v in cpu_baseline_sample(args.workload, seconds_budget=25.0, frames=args.ref_frames).items() if k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as e:  # the oracle is a checker; its absence must not hide the GPU number
             line["cpu_baseline"] = {"error": str(e)}
+    if world == 1 and not args.skip_pose_opt:
+        # metric (ii): pose-optimisation wall-clock through the reference-facing module (lib_python) on a 300-frame directory on disk
+        try:
+            P.close()
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_pose_opt
+            line["pose_opt_wallclock"] = bench_pose_opt.run(frames=args.pose_opt_frames, max_iterations=args.pose_opt_iterations, autodiff_iterations=1, skip_cpu=args.skip_cpu)
+        except Exception as e:
+            line["pose_opt_wallclock"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -358,6 +371,10 @@ def main():
     ap.add_argument("--e2e-iters", type=int, default=20)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-pose-opt", action="store_true", help="skip metric (ii), the lib_python normalizeDepth + optimizePoses wall-clock on a directory on disk")
+    ap.add_argument("--pose-opt-frames", type=int, default=300)
+    ap.add_argument("--pose-opt-iterations", type=int, default=10, help="LM iteration cap per solve of the pose-opt wall-clock run (GPU and CPU replay alike)")
+    ap.add_argument("--no-dist", action="store_true", help="A/B at N > 1: round-1 scheme (all-reduce of H, factorisation replicated on every rank)")
     ap.add_argument("--legacy-update", action="store_true", help="A/B: round-1 cp.async update GEMM instead of the TMA-fed persistent kernel")
     ap.add_argument("--side-ipc", type=int, default=0, help="A/B: items-per-CTA cap of the overlapped (side-stream) update launches")
     ap.add_argument("--skip-cpu", action="store_true")

@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_segmented_sort.cuh>
 #include "rcvd_eval.cuh"
 #include "rcvd_linalg.cuh"
 #include "rcvd_update.cuh"
@@ -30,10 +31,13 @@ using namespace rcvd;
 #define RCVD_API extern "C" __attribute__((visibility("default")))
 
 constexpr int kFastSmem = (3 * kTile * kJsLd + 4 * 256) * (int)sizeof(double);
+static bool run_path_ok_host(const rcvd_config& c, const Layout& L);
 static bool fast_path_ok_host(const rcvd_config& c, const Layout& L) {
   return L.k == 1 && c.spatial_type == RCVD_SPATIAL_IDENTITY && c.intr_opt != RCVD_INTR_SHARED && !c.fix_poses && !c.fix_depth_xforms &&
          !c.fix_spatial_xforms && (c.depth_type != RCVD_DEPTH_GRID || !c.depth_cubic);
 }
+
+static bool run_path_ok_host(const rcvd_config& c, const Layout& L) { return fast_path_ok_host(c, L) && c.depth_type == RCVD_DEPTH_GRID && L.G < 65535; }
 
 static thread_local std::string g_err = "";
 static int set_err(int code, const char* fmt, ...) {
@@ -61,6 +65,10 @@ static int (*CommInitRank)(Comm*, int, UniqueId, int) = nullptr;
 static int (*AllReduce)(const void*, void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
 static int (*CommDestroy)(Comm) = nullptr;
 static const char* (*GetErrorString)(int) = nullptr;
+static int (*GroupStart)() = nullptr;
+static int (*GroupEnd)() = nullptr;
+static int (*Broadcast)(const void*, void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+static int (*Reduce)(const void*, void*, size_t, int, int, int, Comm, cudaStream_t) = nullptr;
 static bool load() {
   if (lib) return true;
   const char* names[] = {"libnccl.so.2", "libnccl.so"};
@@ -71,9 +79,12 @@ static bool load() {
   AllReduce = (int (*)(const void*, void*, size_t, int, int, Comm, cudaStream_t))dlsym(lib, "ncclAllReduce");
   CommDestroy = (int (*)(Comm))dlsym(lib, "ncclCommDestroy");
   GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
-  return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
+  GroupStart = (int (*)())dlsym(lib, "ncclGroupStart"); GroupEnd = (int (*)())dlsym(lib, "ncclGroupEnd");
+  Broadcast = (int (*)(const void*, void*, size_t, int, int, Comm, cudaStream_t))dlsym(lib, "ncclBroadcast");
+  Reduce = (int (*)(const void*, void*, size_t, int, int, int, Comm, cudaStream_t))dlsym(lib, "ncclReduce");
+  return GetUniqueId && CommInitRank && AllReduce && CommDestroy && GroupStart && GroupEnd && Broadcast && Reduce;
 }
-constexpr int kFloat64 = 8, kSum = 0;   // ncclFloat64, ncclSum
+constexpr int kFloat64 = 8, kUint8 = 1, kSum = 0, kMax = 2;   // ncclFloat64, ncclUint8, ncclSum, ncclMax
 }  // namespace nccl
 
 // ---- small vector kernels of the LM loop ----
@@ -171,7 +182,7 @@ __global__ void k_project_state(rcvd_config cfg, Layout L, const uint8_t* __rest
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < N * L.nf) x[i] = project_lb(cfg, L, in_range, i / L.nf, i % L.nf, x[i]);
 }
-__global__ void k_h_to_dense(const double* __restrict__ H, const HBlock* __restrict__ hb, int nblocks, double* __restrict__ out, int N, int nf, int npad) {
+__global__ void k_h_to_dense(const double* __restrict__ H, const HBlock* __restrict__ hb, int nblocks, double* __restrict__ out, int N, int nf, int npad, const int* __restrict__ uperm) {
   const int b = blockIdx.y;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nf * nf) return;
@@ -180,12 +191,13 @@ __global__ void k_h_to_dense(const double* __restrict__ H, const HBlock* __restr
   if (hbk.r == hbk.c && j > i) return;
   const double v = H[(size_t)b * npad * npad + (size_t)i * npad + j];
   const size_t U = (size_t)N * nf;
-  out[((size_t)hbk.r * nf + i) * U + (size_t)hbk.c * nf + j] = v;
-  out[((size_t)hbk.c * nf + j) * U + (size_t)hbk.r * nf + i] = v;
+  const int ur = uperm[hbk.r], uc = uperm[hbk.c];          // internal -> caller's frame order
+  out[((size_t)ur * nf + i) * U + (size_t)uc * nf + j] = v;
+  out[((size_t)uc * nf + j) * U + (size_t)ur * nf + i] = v;
 }
 
 // ---------------------------------------------------------------------------
-struct Level { int frame_off, nframes; int trsm_off, ntrsm; int upd_off, nupd; int upd2_off, nupd2; int fwd_off, nfwd; int it_off, nit, it2_off, nit2; };   // upd: targets consumed by the next level; upd2: the rest
+struct Level { int frame_off, nframes; int trsm_off, ntrsm; int upd_off, nupd; int upd2_off, nupd2; int fwd_off, nfwd; int it_off, nit, it2_off, nit2; int own_off, nown; };   // frame_off: every frame of the level (substitution); own_off: the frames this rank factors   // upd: targets consumed by the next level; upd2: the rest
 
 struct rcvd_problem {
   rcvd_config cfg; Layout L; int N = 0; int device = 0;
@@ -227,8 +239,13 @@ struct rcvd_problem {
   std::vector<void*> allocs;
   // kernel-class profiling (rcvd_debug_profile_linear): when set, enqueue_factor_solve records one event per launch
   std::vector<std::pair<int, cudaEvent_t>>* prof = nullptr;
+  // distributed factorisation (nranks > 1): ownership, internal frame numbering, broadcast / reduce segments
+  bool use_runs = true, records_sorted = false;   // run path of the accumulate kernel (bilinear depth grid): records sorted by cell pair
+  bool dist_enabled = true, dist = false, identity_perm = true, graph_warm = false, force_full_H = false; int LB = 0;
+  std::vector<int> uperm, iperm, fa_off, fa_cnt, fb_off, fb_cnt, tseg, bseg, hseg;   // *_off/_cnt: per-owner frame ranges (phase A / B); segs: (first, count) pairs
+  int *d_lvl_own = nullptr, *d_own_lblocks = nullptr, *d_own_hblocks = nullptr, *d_uperm = nullptr; int n_own_l = 0, n_own_h = 0;
   // TMA-fed persistent update kernel (rcvd_update.cuh)
-  UpdItem* d_upd_items = nullptr; CUtensorMap tmapT; bool gemm_tma = true, tmap_ok = false; int upd_rb = 0, upd_neff = 0, num_sms = 148, upd_ipc = 0;
+  UpdItem* d_upd_items = nullptr; CUtensorMap tmapT; bool gemm_tma = true, tmap_ok = false; int upd_rb = 0, upd_neff = 0, num_sms = 148, upd_ipc = 0, upd_dbg = 0;
   double upd_flops = 0.0;   // algorithmic flops of the update GEMMs of one factorisation (2 nf^3 per product, nf^2 (nf+1) on symmetric targets)
   rcvd_problem() {}
 };
@@ -317,21 +334,88 @@ static int build_structure(rcvd_problem* p) {
     }
     for (int f = 0; f < N; ++f) std::sort(cs[f].begin(), cs[f].end(), [&](int a, int b) { return pos[a] < pos[b]; });
   }
-  // L off-diagonal blocks (r later than c)
+  // levels
+  std::vector<int> lvl(N, 0); int nl = 0;
+  for (int k : order) { for (int a : cs[k]) lvl[a] = std::max(lvl[a], lvl[k] + 1); nl = std::max(nl, lvl[k] + 1); }
+  std::vector<std::vector<int>> lf(nl);
+  for (int k : order) lf[lvl[k]].push_back(k);
+
+  // ---- multi-GPU distribution of the factorisation ----
+  // Phase A = the wide early levels (throughput-bound: thousands of block products): every frame (= block column of the factor) has an
+  // owner rank that factors it (potrf, trsm) and computes every update INTO its column; after the trsm of a level the new off-diagonal
+  // factor blocks X_rk are broadcast from their owners (they are the operands of everybody's updates and of the replicated
+  // substitution).  Phase B = the tail of narrow levels (< 3 frames per level: a latency chain that does not shard) is replicated:
+  // at the boundary every owner broadcasts its trailing blocks.  H is reduced to the owners only (no all-reduce of the matrix).
+  const int R = p->nranks;
+  bool dist = R > 1 && p->dist_enabled && p->cfg.intr_opt != RCVD_INTR_SHARED && !(p->cfg.position_reg > 0.0) && p->trip_centers.empty();
+  int LB = 0;
+  if (dist) { LB = nl; while (LB > 0 && (int)lf[LB - 1].size() < 3) --LB; if (LB == 0) dist = false; }
+  p->dist = dist; p->LB = LB;
+  std::vector<int> own(N, 0);
+  if (dist) {
+    // incoming update work of every column over the phase-A levels (block products; symmetric targets count half)
+    std::vector<double> tot_in(N, 0.0);
+    for (int l = 0; l < LB; ++l) for (int k : lf[l]) { const auto& m = cs[k]; for (size_t a = 0; a < m.size(); ++a) for (size_t b = 0; b <= a; ++b) tot_in[m[b]] += (a == b) ? 0.5 : 1.0; }
+    std::vector<double> load(R, 0.0);
+    for (int l = 0; l < nl; ++l) {
+      std::vector<int> fr = lf[l];
+      auto w = [&](int k) { return tot_in[k] + (l < LB ? 0.6 * cs[k].size() + 0.3 : 0.0); };   // + its own trsm / potrf
+      std::stable_sort(fr.begin(), fr.end(), [&](int a, int b) { return w(a) > w(b); });
+      for (int k : fr) { int q = 0; for (int t = 1; t < R; ++t) if (load[t] < load[q]) q = t; own[k] = q; load[q] += w(k); }
+    }
+  }
+  // internal frame numbering: owner-major, phase-A frames first -- every per-frame array an owner broadcasts / reduces is one contiguous range
+  std::vector<int> uperm, iperm(N, -1);
+  p->fa_off.assign(R, 0); p->fa_cnt.assign(R, 0); p->fb_off.assign(R, 0); p->fb_cnt.assign(R, 0);
+  for (int q = 0; q < R; ++q) for (int ph = 0; ph < 2; ++ph) {
+    (ph ? p->fb_off : p->fa_off)[q] = (int)uperm.size();
+    for (int f = 0; f < N; ++f) if (own[f] == q && ((lvl[f] >= LB) == (ph == 1))) uperm.push_back(f);
+    (ph ? p->fb_cnt : p->fa_cnt)[q] = (int)uperm.size() - (ph ? p->fb_off : p->fa_off)[q];
+  }
+  for (int i = 0; i < N; ++i) iperm[uperm[i]] = i;
+  p->identity_perm = true; for (int i = 0; i < N; ++i) if (uperm[i] != i) p->identity_perm = false;
+  p->uperm = uperm; p->iperm = iperm;
+  if (!p->identity_perm) {
+    auto I = [&](int f) { return iperm[f]; };
+    std::vector<int> order2(N), pos2(N), lvl2(N), own2(N); std::vector<std::vector<int>> cs2(N); std::vector<std::set<int>> orig2(N);
+    for (int i = 0; i < N; ++i) order2[i] = I(order[i]);
+    for (int f = 0; f < N; ++f) { pos2[I(f)] = pos[f]; lvl2[I(f)] = lvl[f]; own2[I(f)] = own[f]; for (int a : cs[f]) cs2[I(f)].push_back(I(a)); for (int a : orig[f]) orig2[I(f)].insert(I(a)); }
+    for (auto& v : lf) for (int& k : v) k = I(k);
+    order.swap(order2); pos.swap(pos2); lvl.swap(lvl2); own.swap(own2); cs.swap(cs2); orig.swap(orig2);
+  }
+  // L off-diagonal blocks (r later than c).  Phase A: level-major, owner-major inside a level (what a rank produces in one level is one
+  // contiguous range of T); phase B: owner-major (what a rank owns of the trailing matrix is one contiguous range of L).
   std::map<std::pair<int, int>, int> lid; int nLoff = 0;
   std::vector<int> lcol;   // column (earlier-eliminated) frame of each off-diagonal factor block
-  for (int k : order) for (int r : cs[k]) { lid[{r, k}] = N + nLoff++; lcol.push_back(k); }
+  auto number_col = [&](int k) { for (int r : cs[k]) { lid[{r, k}] = N + nLoff++; lcol.push_back(k); } };
+  p->tseg.assign((size_t)std::max(LB, 0) * R * 2, 0); p->bseg.assign((size_t)R * 2, 0);
+  for (int l = 0; l < LB; ++l) for (int q = 0; q < R; ++q) {
+    const int first = nLoff;
+    for (int k : lf[l]) if (own[k] == q) number_col(k);
+    p->tseg[((size_t)l * R + q) * 2] = first; p->tseg[((size_t)l * R + q) * 2 + 1] = nLoff - first;
+  }
+  for (int q = 0; q < R; ++q) {
+    const int first = nLoff;
+    for (int l = LB; l < nl; ++l) for (int k : lf[l]) if (own[k] == q) number_col(k);
+    p->bseg[(size_t)q * 2] = first; p->bseg[(size_t)q * 2 + 1] = nLoff - first;
+  }
   p->nLoff = nLoff;
-  // H blocks: diagonal first, then original off-diagonals oriented (later, earlier)
+  // H blocks: diagonal first (internal frame order = owner-major), then original off-diagonals oriented (later, earlier), owner-major
   p->hblocks.clear();
   std::vector<int32_t> blk_of((size_t)N * N, -1);
   for (int f = 0; f < N; ++f) p->hblocks.push_back({f, f, f});
-  for (int a = 0; a < N; ++a) for (int b : orig[a]) if (a < b) {
-    const int r = pos[a] > pos[b] ? a : b, c = pos[a] > pos[b] ? b : a;
-    const int hid = (int)p->hblocks.size();
-    p->hblocks.push_back({lid[{r, c}], r, c});
-    blk_of[(size_t)r * N + c] = hid * 2 + 1;   // (fa = r) is the row side
-    blk_of[(size_t)c * N + r] = hid * 2 + 0;
+  p->hseg.assign((size_t)R * 2, 0);
+  for (int q = 0; q < R; ++q) {
+    p->hseg[(size_t)q * 2] = (int)p->hblocks.size();
+    for (int a = 0; a < N; ++a) for (int b : orig[a]) if (a < b) {
+      const int r = pos[a] > pos[b] ? a : b, c = pos[a] > pos[b] ? b : a;
+      if (own[c] != q) continue;
+      const int hid = (int)p->hblocks.size();
+      p->hblocks.push_back({lid[{r, c}], r, c});
+      blk_of[(size_t)r * N + c] = hid * 2 + 1;   // (fa = r) is the row side
+      blk_of[(size_t)c * N + r] = hid * 2 + 0;
+    }
+    p->hseg[(size_t)q * 2 + 1] = (int)p->hblocks.size() - p->hseg[(size_t)q * 2];
   }
   p->nHblocks = (int)p->hblocks.size();
   // all L blocks with their H source (or -1)
@@ -339,13 +423,13 @@ static int build_structure(rcvd_problem* p) {
   for (int f = 0; f < N; ++f) lblocks[f] = {f, f, f};
   for (auto& kv : lid) lblocks[kv.second] = {-1, kv.first.first, kv.first.second};
   for (int h = N; h < p->nHblocks; ++h) lblocks[p->hblocks[h].lblk].lblk = h;
-  // levels
-  std::vector<int> lvl(N, 0); int nl = 0;
-  for (int k : order) { for (int a : cs[k]) lvl[a] = std::max(lvl[a], lvl[k] + 1); nl = std::max(nl, lvl[k] + 1); }
-  std::vector<std::vector<int>> lf(nl);
-  for (int k : order) lf[lvl[k]].push_back(k);
+  // blocks this rank owns: what it loads into the factor and what it multiplies in the model term (all of them without distribution)
+  std::vector<int> own_lblocks, own_hblocks;
+  for (int b = 0; b < N + nLoff; ++b) { const int c = b < N ? b : lcol[b - N]; if (!dist || own[c] == p->rank) own_lblocks.push_back(b); }
+  for (int h = 0; h < p->nHblocks; ++h) if (!dist || own[p->hblocks[h].c] == p->rank) own_hblocks.push_back(h);
+  p->n_own_l = (int)own_lblocks.size(); p->n_own_h = (int)own_hblocks.size();
   double upd_flops = 0.0;
-  std::vector<int> lvl_frames; std::vector<GemmTask> trsm_tasks, upd_tasks; std::vector<int2> trsm_pairs, upd_pairs;
+  std::vector<int> lvl_frames, lvl_own; std::vector<GemmTask> trsm_tasks, upd_tasks; std::vector<int2> trsm_pairs, upd_pairs;
   std::vector<SolveTask> fwd_tasks, col_tasks; std::vector<int> col_ptr(N + 1, 0); std::vector<TrsmTask> trsm_ll;
   std::vector<UpdItem> upd_items;
   // tile cut of the update targets: as few tiles of <= kUpdMaxTile rows as cover the unknowns (rounded to 8), equal sizes
@@ -355,24 +439,31 @@ static int build_structure(rcvd_problem* p) {
   p->upd_rb = upd_tile; p->upd_neff = upd_neff;
   p->levels.clear();
   for (int l = 0; l < nl; ++l) {
-    Level lv; lv.frame_off = (int)lvl_frames.size(); lv.nframes = (int)lf[l].size();
+    Level lv; lv.frame_off = (int)lvl_frames.size(); lv.nframes = (int)lf[l].size(); lv.own_off = (int)lvl_own.size();
     lv.trsm_off = (int)trsm_tasks.size(); lv.upd_off = (int)upd_tasks.size(); lv.fwd_off = (int)fwd_tasks.size();
     std::map<int, std::vector<int2>> upd;   // target L block id -> source pairs
+    const bool shared_level = !dist || l >= LB;   // replicated work: every rank does all of it
     for (int k : lf[l]) {
       lvl_frames.push_back(k);
+      const bool mine = shared_level || own[k] == p->rank;
+      if (mine) lvl_own.push_back(k);
       for (int r : cs[k]) {
         const int id = lid[{r, k}];
-        trsm_tasks.push_back({id - N, (int)trsm_pairs.size(), 1, 2});
-        trsm_pairs.push_back(make_int2(id, k));
-        trsm_ll.push_back({id - N, id, k});
+        if (mine) {
+          trsm_tasks.push_back({id - N, (int)trsm_pairs.size(), 1, 2});
+          trsm_pairs.push_back(make_int2(id, k));
+          trsm_ll.push_back({id - N, id, k});
+        }
         fwd_tasks.push_back({id - N, r, k});
       }
       for (size_t a = 0; a < cs[k].size(); ++a) for (size_t b = 0; b <= a; ++b) {
-        const int r = cs[k][a], c = cs[k][b];
+        const int r = cs[k][a], c = cs[k][b];                     // c is eliminated before r: the target lives in column c
+        if (!shared_level && own[c] != p->rank) continue;
         const int target = (r == c) ? r : lid[{r, c}];
         upd[target].push_back(make_int2(lid[{r, k}] - N, lid[{c, k}] - N));
       }
     }
+    lv.nown = (int)lvl_own.size() - lv.own_off;
     // targets whose column frame is eliminated in the very next level must be complete before that level starts (critical);
     // all other updates may overlap the next level's potrf / inverse / trsm on a second stream.
     for (int pass = 0; pass < 2; ++pass) {
@@ -413,7 +504,8 @@ static int build_structure(rcvd_problem* p) {
   int rc;
 #define UP(ptr, vec) if ((rc = upload(p, &(ptr), vec))) return rc
   p->upd_flops = upd_flops;
-  UP(p->d_blk_of, blk_of); UP(p->d_hblocks, p->hblocks); UP(p->d_lblocks, lblocks); UP(p->d_lvl_frames, lvl_frames);
+  UP(p->d_blk_of, blk_of); UP(p->d_hblocks, p->hblocks); UP(p->d_lblocks, lblocks); UP(p->d_lvl_frames, lvl_frames); UP(p->d_lvl_own, lvl_own);
+  UP(p->d_own_lblocks, own_lblocks); UP(p->d_own_hblocks, own_hblocks); UP(p->d_uperm, p->uperm);
   UP(p->d_trsm_tasks, trsm_tasks); UP(p->d_upd_tasks, upd_tasks); UP(p->d_trsm_pairs, trsm_pairs); UP(p->d_upd_pairs, upd_pairs);
   UP(p->d_fwd_tasks, fwd_tasks); UP(p->d_col_tasks, col_tasks); UP(p->d_col_ptr, col_ptr); UP(p->d_trsm_ll, trsm_ll); UP(p->d_upd_items, upd_items);
   // tiles
@@ -423,7 +515,29 @@ static int build_structure(rcvd_problem* p) {
     for (int64_t b = p->offsets[i]; b < p->offsets[i + 1]; b += kTile) { tile_pair.push_back(i); tile_begin.push_back(b); tile_count.push_back((int32_t)std::min<int64_t>(kTile, p->offsets[i + 1] - b)); }
   p->num_tiles = (int)tile_pair.size(); p->C = p->offsets.empty() ? 0 : p->offsets.back();
   UP(p->d_tile_pair, tile_pair); UP(p->d_tile_begin, tile_begin); UP(p->d_tile_count, tile_count);
-  UP(p->d_pair_frames, p->pair_frames); UP(p->d_records, p->records_h);
+  {
+    std::vector<int32_t> pf_int(p->pair_frames.size());
+    for (size_t i = 0; i < pf_int.size(); ++i) pf_int[i] = p->iperm[p->pair_frames[i]];
+    UP(p->d_pair_frames, pf_int); UP(p->d_records, p->records_h);
+  }
+  p->records_sorted = false;
+  if (p->use_runs && run_path_ok_host(p->cfg, L) && p->C > 0 && p->C < (int64_t)0x7fffffff) {
+    // run path of the accumulate kernel: the records of every pair sorted by (source cell, target cell) -- device segmented sort by pair
+    const long long n = p->C;
+    unsigned *d_k0 = nullptr, *d_k1 = nullptr; int *d_i0 = nullptr, *d_i1 = nullptr; float* d_sorted = nullptr; int64_t* d_off = nullptr; void* d_tmp = nullptr;
+    int rcs;
+    if ((rcs = dalloc(p, &d_k0, (size_t)n)) || (rcs = dalloc(p, &d_k1, (size_t)n)) || (rcs = dalloc(p, &d_i0, (size_t)n)) || (rcs = dalloc(p, &d_i1, (size_t)n)) || (rcs = dalloc(p, &d_sorted, (size_t)n * 6)) ||
+        (rcs = upload(p, &d_off, p->offsets))) return rcs;
+    k_record_keys<<<(unsigned)((n + 255) / 256), 256, 0, p->stream>>>(p->cfg, p->d_records, n, d_k0, d_i0);
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceSegmentedSort::SortPairs(nullptr, tmp_bytes, d_k0, d_k1, d_i0, d_i1, (int)n, np, d_off, d_off + 1, p->stream));
+    CK(cudaMallocAsync(&d_tmp, std::max<size_t>(tmp_bytes, 16), p->stream));
+    CK(cub::DeviceSegmentedSort::SortPairs(d_tmp, tmp_bytes, d_k0, d_k1, d_i0, d_i1, (int)n, np, d_off, d_off + 1, p->stream));
+    k_gather_records<<<(unsigned)((n * 6 + 255) / 256), 256, 0, p->stream>>>(p->d_records, d_i1, n, d_sorted);
+    CK(cudaFreeAsync(d_tmp, p->stream));
+    CK(cudaGetLastError());
+    p->d_records = d_sorted; p->records_sorted = true;      // (the unsorted copy and the sort buffers go back to the pool with the handle's other allocations)
+  }
   {
     std::vector<int32_t> tc, tn; std::vector<int64_t> tb;
     for (size_t i = 0; i < p->trip_centers.size(); ++i)
@@ -431,8 +545,16 @@ static int build_structure(rcvd_problem* p) {
     p->num_trip_tiles = (int)tc.size();
     UP(p->d_trip_tile_center, tc); UP(p->d_trip_tile_begin, tb); UP(p->d_trip_tile_count, tn); UP(p->d_trip_records, p->trip_records);
   }
-  UP(p->d_in_range, p->in_range); UP(p->d_median, p->median);
-  if (!p->adaptive.empty()) UP(p->d_adaptive, p->adaptive);
+  {
+    std::vector<uint8_t> ir(N); std::vector<double> md(N), ad;
+    for (int i = 0; i < N; ++i) { ir[i] = p->in_range[p->uperm[i]]; md[i] = p->median[p->uperm[i]]; }
+    UP(p->d_in_range, ir); UP(p->d_median, md);
+    if (!p->adaptive.empty()) {
+      const size_t G = p->adaptive.size() / N; ad.resize(p->adaptive.size());
+      for (int i = 0; i < N; ++i) std::copy(p->adaptive.begin() + (size_t)p->uperm[i] * G, p->adaptive.begin() + (size_t)(p->uperm[i] + 1) * G, ad.begin() + (size_t)i * G);
+      UP(p->d_adaptive, ad);
+    }
+  }
   {
     // scale-regulariser lattice in float32, lib/PoseOptimizer.cpp:1382-1385
     std::vector<float> locs; const int gx = p->cfg.scale_grid_x, gy = p->cfg.scale_grid_y;
@@ -451,7 +573,8 @@ static int build_structure(rcvd_problem* p) {
   const size_t Upad = (size_t)N * npad, U = (size_t)N * L.nf;
 #define DA(ptr, n) if ((rc = dalloc(p, &(ptr), (n)))) return rc
   DA(p->d_x, U); DA(p->d_xc, U); DA(p->d_xsave, U);
-  DA(p->d_g, Upad + 8); DA(p->d_S, Upad); DA(p->d_diagH, Upad); DA(p->d_lmdiag, Upad); DA(p->d_D2, Upad); DA(p->d_gs, Upad); DA(p->d_rhs, Upad);
+  DA(p->d_g, 2 * Upad + 8); p->d_diagH = p->d_g + Upad + 8;   // [gradient | 8 scalars | diag H]: one packed all-reduce at N > 1
+  DA(p->d_S, Upad); DA(p->d_lmdiag, Upad); DA(p->d_D2, Upad); DA(p->d_gs, Upad); DA(p->d_rhs, Upad);
   DA(p->d_g2, Upad + 8); DA(p->d_delta, Upad);
   DA(p->d_ytmp, Upad); DA(p->d_y, Upad); DA(p->d_Sy, Upad); DA(p->d_Hy, Upad); DA(p->d_scal, SC_N); DA(p->d_active, Upad); DA(p->d_fail, 1);
   const RegCounts rcn = reg_counts(p->cfg, L, N, p->nscale);
@@ -496,15 +619,44 @@ static int build_structure(rcvd_problem* p) {
   if (p->num_trip_tiles > 0) k_triplets<2><<<p->num_trip_tiles, kTile, 0, p->stream>>>(d, p->d_x, nullptr, nullptr, nullptr, p->d_active);
   k_finalize_mask<<<(int)((Upad + 255) / 256), 256, 0, p->stream>>>(p->cfg, L, p->d_active, N);
   CK(cudaGetLastError());
+  if (p->nranks > 1) {   // the parameter set of the program is the union over the ranks' constraint shards (norms and stopping tests must agree on every rank)
+    const int r = nccl::AllReduce(p->d_active, p->d_active, Upad, nccl::kUint8, nccl::kMax, p->comm, p->stream);
+    if (r != 0) return set_err(RCVD_ERR_NCCL, "ncclAllReduce(active mask) failed");
+  }
   // kernels that need > 48 KB dynamic smem
   if ((npad * 16 + 16 * (npad + 1)) * (int)sizeof(double) > 220 * 1024) return set_err(RCVD_ERR_INVALID, "frame block too large for the panel-inverse kernel (npad=%d)", npad);
   CK(cudaFuncSetAttribute(k_trinv, cudaFuncAttributeMaxDynamicSharedMemorySize, (npad * 16 + 16 * (npad + 1)) * (int)sizeof(double)));
   CK(cudaFuncSetAttribute(k_accumulate_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem));
+  CK(cudaFuncSetAttribute(k_accumulate_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, kRunSmem));
   p->use_trsm_ll = p->allow_trsm_ll && trsm_ll_smem_bytes(npad) <= 220 * 1024;
   if (p->use_trsm_ll) CK(cudaFuncSetAttribute(k_trsm_ll, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_ll_smem_bytes(npad)));
   if (potrf_smem_bytes(npad) <= 220 * 1024) CK(cudaFuncSetAttribute(k_potrf_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_smem_bytes(npad)));
   CK(cudaStreamSynchronize(p->stream));
   p->structure_ready = true;
+  return RCVD_OK;
+}
+
+static int allreduce(rcvd_problem* p, double* buf, size_t count) {
+  if (p->nranks <= 1) return RCVD_OK;
+  const int r = nccl::AllReduce(buf, buf, count, nccl::kFloat64, nccl::kSum, p->comm, p->stream);
+  if (r != 0) return set_err(RCVD_ERR_NCCL, "ncclAllReduce failed: %s", nccl::GetErrorString ? nccl::GetErrorString(r) : "?");
+  return RCVD_OK;
+}
+// One fused NCCL launch: for every rank q, segs[q] = (first, count) in units of `unit` doubles of `base` is broadcast from q (bcast) or
+// summed onto q (!bcast), in place.  Every rank passes identical segments.
+struct Seg { size_t first, count; };
+static int grouped(rcvd_problem* p, double* base, size_t unit, const std::vector<Seg>& segs, bool bcast) {
+  int r = nccl::GroupStart();
+  for (size_t i = 0; i < segs.size() && r == 0; ++i) {
+    if (segs[i].count == 0) continue;
+    const int root = (int)(i % (size_t)p->nranks);
+    double* ptr = base + segs[i].first * unit;
+    r = bcast ? nccl::Broadcast(ptr, ptr, segs[i].count * unit, nccl::kFloat64, root, p->comm, p->stream)
+              : nccl::Reduce(ptr, ptr, segs[i].count * unit, nccl::kFloat64, nccl::kSum, root, p->comm, p->stream);
+  }
+  const int r2 = nccl::GroupEnd();
+  if (r == 0) r = r2;
+  if (r != 0) return set_err(RCVD_ERR_NCCL, "grouped NCCL %s failed: %s", bcast ? "broadcast" : "reduce", nccl::GetErrorString ? nccl::GetErrorString(r) : "?");
   return RCVD_OK;
 }
 
@@ -524,24 +676,39 @@ static int enqueue_factor_solve(rcvd_problem* p) {
     k_gemm_nt<<<dim3(tiles, tiles, ntasks), 128, 0, cs>>>(dstp, A, B, tasks, prs, npad, beta != 0.0 ? neff : npad, alpha, beta);
   };
   mark(-1);
-  k_load_factor<<<dim3((npad * npad + 255) / 256, nL), 256, 0, st>>>(p->d_H, p->d_Lb, p->d_lblocks, p->d_S, p->d_D2, npad, L.nf);
+  k_load_factor<<<dim3((npad * npad + 255) / 256, p->dist ? p->n_own_l : nL), 256, 0, st>>>(p->d_H, p->d_Lb, p->d_lblocks, p->d_S, p->d_D2, npad, L.nf, p->dist ? p->d_own_lblocks : nullptr);
   p->launches += 1; mark(P_LOAD);
   // Two-stream schedule (fork/join inside the captured graph): the non-critical update GEMMs of level l run on `side`
   // concurrently with potrf / inverse / trsm of level l+1 on `st`.
   cudaStream_t side = p->side_stream;
   bool side_pending = false, side_used = false;
+  const size_t bsz = (size_t)npad * npad;
+  // phase boundary of the distributed factorisation: the owners' explicit inverses (for the replicated substitution) and their
+  // blocks of the trailing matrix go to everybody; from here on every rank factors the same narrow tail
+  auto phase_boundary = [&]() -> int {
+    if (side_pending || side_used) { CK(cudaEventRecord(p->ev_join, side)); CK(cudaStreamWaitEvent(st, p->ev_join, 0)); side_pending = false; }
+    std::vector<Seg> inv, tr;
+    for (int q = 0; q < p->nranks; ++q) inv.push_back({(size_t)p->fa_off[q], (size_t)p->fa_cnt[q]});
+    for (int q = 0; q < p->nranks; ++q) tr.push_back({(size_t)p->fb_off[q], (size_t)p->fb_cnt[q]});
+    for (int q = 0; q < p->nranks; ++q) tr.push_back({(size_t)N + (size_t)p->bseg[2 * q], (size_t)p->bseg[2 * q + 1]});
+    int rc = grouped(p, p->d_invL, bsz, inv, true); if (rc) return rc;
+    return grouped(p, p->d_Lb, bsz, tr, true);
+  };
   for (size_t li = 0; li < p->levels.size(); ++li) {
     const Level& lv = p->levels[li];
+    if (p->dist && (int)li == p->LB) { int rc = phase_boundary(); if (rc) return rc; }
+    const int* lframes = p->d_lvl_own + lv.own_off; const int nfr = lv.nown;      // the frames this rank factors at this level
+    if (nfr > 0) {
     if (potrf_smem_bytes(npad) <= 220 * 1024)
-      k_potrf_smem<<<lv.nframes, kPotrfSmemThreads, potrf_smem_bytes(npad), st>>>(p->d_Lb, p->d_invT, p->d_lvl_frames + lv.frame_off, npad, p->d_fail, p->potrf_chain_warp ? 1 : 0);
+      k_potrf_smem<<<nfr, kPotrfSmemThreads, potrf_smem_bytes(npad), st>>>(p->d_Lb, p->d_invT, lframes, npad, p->d_fail, p->potrf_chain_warp ? 1 : 0);
     else {
       // large blocks: 16-wide panels, panel factor on one CTA per frame, trailing update on the whole machine
       const int nt16 = npad / 16;
       for (int jb = 0; jb < nt16; ++jb) {
-        k_potrf_panel<<<lv.nframes, kPotrfThreads, 0, st>>>(p->d_Lb, p->d_invT, p->d_lvl_frames + lv.frame_off, npad, jb, p->d_fail);
+        k_potrf_panel<<<nfr, kPotrfThreads, 0, st>>>(p->d_Lb, p->d_invT, lframes, npad, jb, p->d_fail);
         p->launches += 1;
         const int m = npad - (jb + 1) * 16;
-        if (m > 0) { const int n64 = (m + 63) / 64; k_potrf_trail<<<dim3(n64 * (n64 + 1) / 2, lv.nframes), 128, 0, st>>>(p->d_Lb, p->d_lvl_frames + lv.frame_off, npad, jb); p->launches += 1; }
+        if (m > 0) { const int n64 = (m + 63) / 64; k_potrf_trail<<<dim3(n64 * (n64 + 1) / 2, nfr), 128, 0, st>>>(p->d_Lb, lframes, npad, jb); p->launches += 1; }
       }
       p->launches -= 1;   // (the common increment below)
     }
@@ -550,13 +717,20 @@ static int enqueue_factor_solve(rcvd_problem* p) {
       // the explicit inverse is only needed by the (much later) substitution phase: compute it off the critical path
       cudaStream_t is = st;
       if (p->overlap) { CK(cudaEventRecord(p->ev_fork, st)); CK(cudaStreamWaitEvent(side, p->ev_fork, 0)); is = side; side_used = true; }
-      k_trinv<<<dim3(npad / 16, lv.nframes), 256, (npad * 16 + 16 * (npad + 1)) * sizeof(double), is>>>(p->d_Lb, p->d_invT, p->d_invL, p->d_lvl_frames + lv.frame_off, npad);
+      k_trinv<<<dim3(npad / 16, nfr), 256, (npad * 16 + 16 * (npad + 1)) * sizeof(double), is>>>(p->d_Lb, p->d_invT, p->d_invL, lframes, npad);
       p->launches += 1; mark(P_TRINV);
       if (lv.ntrsm > 0) { k_trsm_ll<<<dim3((npad + kTrsmStrip - 1) / kTrsmStrip, lv.ntrsm), 128, trsm_ll_smem_bytes(npad), st>>>(p->d_T, p->d_Lb, p->d_invT, p->d_trsm_ll + lv.trsm_off, npad); p->launches++; mark(P_TRSM); }
     } else {
-      k_trinv<<<dim3(npad / 16, lv.nframes), 256, (npad * 16 + 16 * (npad + 1)) * sizeof(double), st>>>(p->d_Lb, p->d_invT, p->d_invL, p->d_lvl_frames + lv.frame_off, npad);
+      k_trinv<<<dim3(npad / 16, nfr), 256, (npad * 16 + 16 * (npad + 1)) * sizeof(double), st>>>(p->d_Lb, p->d_invT, p->d_invL, lframes, npad);
       p->launches += 1; mark(P_TRINV);
       if (lv.ntrsm > 0) { gemm(st, lv.ntrsm, p->d_T, p->d_Lb, p->d_invL, p->d_trsm_tasks + lv.trsm_off, p->d_trsm_pairs, 1.0, 0.0); p->launches++; mark(P_TRSM); }
+    }
+    }
+    if (p->dist && (int)li < p->LB) {
+      // the off-diagonal factor blocks of this level, from their owners to everybody (one fused NCCL launch)
+      std::vector<Seg> segs;
+      for (int q = 0; q < p->nranks; ++q) segs.push_back({(size_t)p->tseg[(li * p->nranks + q) * 2], (size_t)p->tseg[(li * p->nranks + q) * 2 + 1]});
+      int rc = grouped(p, p->d_T, bsz, segs, true); if (rc) return rc;
     }
     if (lv.nupd2 > 0 && p->overlap) {
       CK(cudaEventRecord(p->ev_fork, st)); CK(cudaStreamWaitEvent(side, p->ev_fork, 0));
@@ -565,7 +739,7 @@ static int enqueue_factor_solve(rcvd_problem* p) {
     auto update = [&](cudaStream_t cs, int off, int n, bool side_launch) {   // persistent TMA-fed update kernel
       int grid = std::min(n, 2 * p->num_sms);
       if (side_launch && p->upd_ipc > 0) grid = std::max(grid, (n + p->upd_ipc - 1) / p->upd_ipc);
-      k_update_tma<<<grid, kUpdThreads, upd_smem_bytes(p->upd_rb), cs>>>(p->tmapT, p->d_Lb, p->d_upd_items + off, n, p->d_upd_pairs, npad, p->upd_neff, p->upd_rb);
+      k_update_tma<<<grid, kUpdThreads, upd_smem_bytes(p->upd_rb), cs>>>(p->tmapT, p->d_Lb, p->d_upd_items + off, n, p->d_upd_pairs, npad, p->upd_neff, p->upd_rb, p->upd_dbg);
     };
     if (p->gemm_tma) {
       if (lv.nit > 0) { update(st, lv.it_off, lv.nit, false); p->launches++; mark(P_GEMM); }
@@ -587,6 +761,7 @@ static int enqueue_factor_solve(rcvd_problem* p) {
       if (p->overlap) { CK(cudaEventRecord(p->ev_join, side)); side_pending = true; side_used = true; }
     }
   }
+  if (p->dist && p->LB >= (int)p->levels.size()) { int rc = phase_boundary(); if (rc) return rc; }
   if (side_pending || side_used) { CK(cudaEventRecord(p->ev_join, side)); CK(cudaStreamWaitEvent(st, p->ev_join, 0)); }
   CK(cudaMemcpyAsync(p->d_rhs, p->d_gs, (size_t)N * npad * sizeof(double), cudaMemcpyDeviceToDevice, st));
   for (const Level& lv : p->levels) {
@@ -609,6 +784,10 @@ static int enqueue_factor_solve(rcvd_problem* p) {
 
 // factor+solve through a CUDA graph (the level schedule is ~5 launches per level)
 static int factor_solve(rcvd_problem* p) {
+  if (p->nranks > 1 && !p->graph_warm) {   // NCCL establishes its connections lazily on first use: not inside a stream capture
+    p->graph_warm = true;
+    return enqueue_factor_solve(p);
+  }
   if (!p->solve_graph) {
     cudaGraph_t graph;
     const int64_t l0 = p->launches;
@@ -631,13 +810,6 @@ static int factor_solve(rcvd_problem* p) {
 // Evaluation
 // ---------------------------------------------------------------------------
 
-static int allreduce(rcvd_problem* p, double* buf, size_t count) {
-  if (p->nranks <= 1) return RCVD_OK;
-  const int r = nccl::AllReduce(buf, buf, count, nccl::kFloat64, nccl::kSum, p->comm, p->stream);
-  if (r != 0) return set_err(RCVD_ERR_NCCL, "ncclAllReduce failed: %s", nccl::GetErrorString ? nccl::GetErrorString(r) : "?");
-  return RCVD_OK;
-}
-
 // Cost (-> d_scal[slot]) at state x; optionally gradient (gout, npad stride) and H.
 static int enqueue_evaluate(rcvd_problem* p, const double* x, bool wantG, bool wantH, double* gout, int slot) {
   const Layout& L = p->L; const int N = p->N, npad = L.npad; cudaStream_t st = p->stream;
@@ -648,7 +820,8 @@ static int enqueue_evaluate(rcvd_problem* p, const double* x, bool wantG, bool w
   if (wantH) CK(cudaMemsetAsync(p->d_H, 0, (size_t)p->nHblocks * bs * sizeof(double), st));
   if (wantG) CK(cudaMemsetAsync(gout, 0, (Upad + 8) * sizeof(double), st));
   if (p->num_tiles > 0) {
-    if (wantH && p->use_fast && fast_path_ok_host(p->cfg, L)) k_accumulate_fast<<<p->num_tiles, kTile, kFastSmem, st>>>(d, x, p->d_H, gout, p->d_partial);
+    if (wantH && p->use_fast && p->records_sorted) k_accumulate_runs<<<p->num_tiles, kTile, kRunSmem, st>>>(d, x, p->d_H, gout, p->d_partial);
+    else if (wantH && p->use_fast && fast_path_ok_host(p->cfg, L)) k_accumulate_fast<<<p->num_tiles, kTile, kFastSmem, st>>>(d, x, p->d_H, gout, p->d_partial);
     else if (wantH) k_accumulate_generic<true><<<p->num_tiles, kTile, 0, st>>>(d, x, p->d_H, gout, p->d_partial);
     else if (wantG) k_accumulate_generic<false><<<p->num_tiles, kTile, 0, st>>>(d, x, nullptr, gout, p->d_partial);
     else k_cost_static<<<p->num_tiles, kTile, 0, st>>>(d, x, p->d_partial);
@@ -673,11 +846,47 @@ static int enqueue_evaluate(rcvd_problem* p, const double* x, bool wantG, bool w
   CK(cudaGetLastError());
   if (p->nranks > 1) {
     int rc;
-    if (wantH && (rc = allreduce(p, p->d_H, (size_t)p->nHblocks * bs))) return rc;
-    if (wantG && (rc = allreduce(p, gout, Upad))) return rc;
-    if ((rc = allreduce(p, p->d_scal + slot, 1))) return rc;
+    if (wantG) {
+      // ONE packed all-reduce: [gradient (Upad) | cost + 7 spare | diagonal of H (Upad, only with H into d_g)]
+      CK(cudaMemcpyAsync(gout + Upad, p->d_scal + slot, sizeof(double), cudaMemcpyDeviceToDevice, st));
+      size_t cnt = Upad + 8;
+      if (wantH && gout == p->d_g) { k_extract_diag<<<(int)((Upad + 255) / 256), 256, 0, st>>>(p->d_H, p->d_diagH, N, npad); p->launches++; cnt = 2 * Upad + 8; }
+      if ((rc = allreduce(p, gout, cnt))) return rc;
+      CK(cudaMemcpyAsync(p->d_scal + slot, gout + Upad, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    } else if ((rc = allreduce(p, p->d_scal + slot, 1))) return rc;
+    if (wantH) {
+      if (p->dist && !p->force_full_H) {
+        // the normal matrix is summed onto the OWNER of every block only (its frames' diagonal blocks, the off-diagonal blocks of its columns)
+        std::vector<Seg> segs;
+        for (int q = 0; q < p->nranks; ++q) segs.push_back({(size_t)p->fa_off[q], (size_t)(p->fa_cnt[q] + p->fb_cnt[q])});
+        for (int q = 0; q < p->nranks; ++q) segs.push_back({(size_t)p->hseg[2 * q], (size_t)p->hseg[2 * q + 1]});
+        if ((rc = grouped(p, p->d_H, bs, segs, false))) return rc;
+      } else if ((rc = allreduce(p, p->d_H, (size_t)p->nHblocks * bs))) return rc;
+    }
   }
   return RCVD_OK;
+}
+
+// Frame-major host vectors in the caller's frame order <-> device vectors in the internal (owner-major) order.
+static int upload_frames(rcvd_problem* p, double* dst, const double* src_user, int stride_dst, int stride_src, int count) {
+  std::vector<double> tmp((size_t)p->N * stride_dst, 0.0);
+  for (int i = 0; i < p->N; ++i) memcpy(tmp.data() + (size_t)i * stride_dst, src_user + (size_t)p->uperm[i] * stride_src, (size_t)count * sizeof(double));
+  CK(cudaMemcpyAsync(dst, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+  CK(cudaStreamSynchronize(p->stream));      // tmp goes out of scope
+  return RCVD_OK;
+}
+static int download_frames(rcvd_problem* p, double* dst_user, const double* src, int stride_dst, int stride_src, int count) {
+  std::vector<double> tmp((size_t)p->N * stride_src);
+  CK(cudaMemcpyAsync(tmp.data(), src, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  for (int i = 0; i < p->N; ++i) memcpy(dst_user + (size_t)p->uperm[i] * stride_dst, tmp.data() + (size_t)i * stride_src, (size_t)count * sizeof(double));
+  return RCVD_OK;
+}
+// device state -> h_state (caller's frame order); used before the structure is rebuilt
+static int save_state(rcvd_problem* p) {
+  DevGuard g(p->device); cudaStreamSynchronize(p->stream);
+  if (p->h_state.size() != (size_t)p->N * p->L.nf) p->h_state.assign((size_t)p->N * p->L.nf, 0.0);
+  return download_frames(p, p->h_state.data(), p->d_x, p->L.nf, p->L.nf, p->L.nf);
 }
 
 static int ensure_ready(rcvd_problem* p) {
@@ -690,7 +899,7 @@ static int ensure_ready(rcvd_problem* p) {
   }
   if (p->state_dirty) {
     if (p->h_state.size() != (size_t)p->N * p->L.nf) p->h_state.assign((size_t)p->N * p->L.nf, 0.0);
-    CK(cudaMemcpyAsync(p->d_x, p->h_state.data(), p->h_state.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    { int rc = upload_frames(p, p->d_x, p->h_state.data(), p->L.nf, p->L.nf, p->L.nf); if (rc) return rc; }
     p->state_dirty = false;
   }
   return RCVD_OK;
@@ -781,8 +990,9 @@ static int enqueue_model_terms(rcvd_problem* p) {
   const int N = p->N, npad = p->L.npad; const size_t Upad = (size_t)N * npad; cudaStream_t st = p->stream;
   k_mul<<<nblk(Upad), 256, 0, st>>>(p->d_S, p->d_y, p->d_Sy, (int)Upad);
   CK(cudaMemsetAsync(p->d_Hy, 0, Upad * sizeof(double), st));
-  k_spmv_sym<<<dim3((npad + 7) / 8, p->nHblocks), 256, 0, st>>>(p->d_H, p->d_hblocks, p->d_Sy, p->d_Hy, npad);
+  k_spmv_sym<<<dim3((npad + 7) / 8, p->dist ? p->n_own_h : p->nHblocks), 256, 0, st>>>(p->d_H, p->d_hblocks, p->d_Sy, p->d_Hy, npad, p->dist ? p->d_own_hblocks : nullptr);
   k_dot2<<<nblk(Upad), 256, 0, st>>>(p->d_gs, p->d_y, p->d_Sy, p->d_Hy, (int)Upad, p->d_scal, SC_GY, SC_YHY);
+  if (p->dist) { int rc = allreduce(p, p->d_scal + SC_YHY, 1); if (rc) return rc; }   // every rank multiplied the H blocks it owns
   k_make_delta<<<nblk(Upad), 256, 0, st>>>(p->d_y, p->d_S, p->d_delta, (int)Upad);
   p->launches += 4;
   return RCVD_OK;
@@ -842,7 +1052,7 @@ static int lm_solve(rcvd_problem* p, const rcvd_solve_options& o, rcvd_solve_sum
     CK(cudaEventRecord(p->ev[0], st));
     int r = enqueue_evaluate(p, p->d_x, true, true, p->d_g, SC_COST); if (r) return r;
     CK(cudaEventRecord(p->ev[1], st));
-    k_extract_diag<<<nblk(Upad), 256, 0, st>>>(p->d_H, p->d_diagH, N, npad);
+    if (p->nranks <= 1) k_extract_diag<<<nblk(Upad), 256, 0, st>>>(p->d_H, p->d_diagH, N, npad);
     k_state_norms<<<nblk(U), 256, 0, st>>>(p->cfg, L, p->d_in_range, p->d_active, p->d_x, p->d_g, p->d_scal, N);
     p->launches += 2;
     r = read_scalars(p); if (r) return r;
@@ -1016,13 +1226,13 @@ RCVD_API int32_t rcvd_problem_set_frames(rcvd_problem* p, const uint8_t* in_rang
   if (median) p->median.assign(median, median + p->N); else p->median.assign(p->N, 1.0);
   if (adaptive && p->cfg.depth_type == RCVD_DEPTH_GRID) p->adaptive.assign(adaptive, adaptive + (size_t)p->N * p->cfg.depth_grid_x * p->cfg.depth_grid_y); else p->adaptive.clear();
   if (p->cfg.adaptive_deform > 0.0 && p->adaptive.empty()) return set_err(RCVD_ERR_INVALID, "adaptive deformation cost requires node weights");
-  if (p->structure_ready) { DevGuard dev_guard_(p->device); cudaStreamSynchronize(p->stream); CK(cudaMemcpy(p->h_state.data(), p->d_x, p->h_state.size() * sizeof(double), cudaMemcpyDeviceToHost)); }
+  if (p->structure_ready) { int rc_ = save_state(p); if (rc_) return rc_; }
   p->structure_ready = false;
   return RCVD_OK;
 }
 RCVD_API int32_t rcvd_problem_set_constraints(rcvd_problem* p, int32_t np, const int32_t* pf, const int64_t* off, const float* rec) {
   if (!p || np < 0 || (np > 0 && (!pf || !off))) return set_err(RCVD_ERR_INVALID, "bad constraint arrays");
-  if (p->structure_ready) { DevGuard dev_guard_(p->device); cudaStreamSynchronize(p->stream); CK(cudaMemcpy(p->h_state.data(), p->d_x, p->h_state.size() * sizeof(double), cudaMemcpyDeviceToHost)); }
+  if (p->structure_ready) { int rc_ = save_state(p); if (rc_) return rc_; }
   p->pair_frames.assign(pf, pf + 2 * (size_t)np);
   if (np > 0) p->offsets.assign(off, off + np + 1); else p->offsets.assign(1, 0);
   for (int i = 0; i < np; ++i) {
@@ -1037,7 +1247,7 @@ RCVD_API int32_t rcvd_problem_set_constraints(rcvd_problem* p, int32_t np, const
 }
 RCVD_API int32_t rcvd_problem_set_triplets(rcvd_problem* p, int32_t nt, const int32_t* centers, const int64_t* off, const float* rec) {
   if (!p || nt < 0 || (nt > 0 && (!centers || !off))) return set_err(RCVD_ERR_INVALID, "bad triplet arrays");
-  if (p->structure_ready) { DevGuard dev_guard_(p->device); cudaStreamSynchronize(p->stream); CK(cudaMemcpy(p->h_state.data(), p->d_x, p->h_state.size() * sizeof(double), cudaMemcpyDeviceToHost)); }
+  if (p->structure_ready) { int rc_ = save_state(p); if (rc_) return rc_; }
   p->trip_centers.assign(centers, centers + nt);
   if (nt > 0) p->trip_offsets.assign(off, off + nt + 1); else p->trip_offsets.assign(1, 0);
   for (int i = 0; i < nt; ++i) if (p->trip_offsets[i + 1] < p->trip_offsets[i] || centers[i] < 1 || centers[i] + 1 >= p->N) return set_err(RCVD_ERR_INVALID, "bad triplet group %d", i);
@@ -1081,9 +1291,7 @@ RCVD_API int32_t rcvd_problem_get_state(rcvd_problem* p, double* x) {
   const size_t U = (size_t)p->N * p->L.nf;
   if (!p->structure_ready || p->state_dirty) { if (p->h_state.size() != U) p->h_state.assign(U, 0.0); memcpy(x, p->h_state.data(), U * sizeof(double)); return RCVD_OK; }
   SET_DEVICE(p->device);
-  CK(cudaMemcpyAsync(x, p->d_x, U * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-  CK(cudaStreamSynchronize(p->stream));
-  return RCVD_OK;
+  return download_frames(p, x, p->d_x, p->L.nf, p->L.nf, p->L.nf);
 }
 RCVD_API int32_t rcvd_evaluate(rcvd_problem* p, double* cost, double* gradient) {
   if (!p || !cost) return set_err(RCVD_ERR_INVALID, "null argument");
@@ -1094,9 +1302,7 @@ RCVD_API int32_t rcvd_evaluate(rcvd_problem* p, double* cost, double* gradient) 
   rc = read_scalars(p); if (rc) return rc;
   *cost = p->h_scal[SC_COST];
   if (gradient) {
-    std::vector<double> g((size_t)p->N * p->L.npad);
-    CK(cudaMemcpy(g.data(), p->d_g, g.size() * sizeof(double), cudaMemcpyDeviceToHost));
-    for (int f = 0; f < p->N; ++f) memcpy(gradient + (size_t)f * p->L.nf, g.data() + (size_t)f * p->L.npad, p->L.nf * sizeof(double));
+    if ((rc = download_frames(p, gradient, p->d_g, p->L.nf, p->L.npad, p->L.nf))) return rc;
   }
   return RCVD_OK;
 }
@@ -1104,12 +1310,15 @@ RCVD_API int32_t rcvd_normal_matrix_dense(rcvd_problem* p, double* Hout) {
   if (!p || !Hout) return set_err(RCVD_ERR_INVALID, "null argument");
   SET_DEVICE(p->device);
   int rc = ensure_ready(p); if (rc) return rc;
-  rc = enqueue_evaluate(p, p->d_x, true, true, p->d_g, SC_COST); if (rc) return rc;
+  p->force_full_H = true;                       // debug view: every rank assembles the whole matrix
+  rc = enqueue_evaluate(p, p->d_x, true, true, p->d_g, SC_COST);
+  p->force_full_H = false;
+  if (rc) return rc;
   const size_t U = (size_t)p->N * p->L.nf;
   double* d_out = nullptr;
   CK(cudaMalloc((void**)&d_out, U * U * sizeof(double)));
   CK(cudaMemsetAsync(d_out, 0, U * U * sizeof(double), p->stream));
-  k_h_to_dense<<<dim3(nblk((size_t)p->L.nf * p->L.nf), p->nHblocks), 256, 0, p->stream>>>(p->d_H, p->d_hblocks, p->nHblocks, d_out, p->N, p->L.nf, p->L.npad);
+  k_h_to_dense<<<dim3(nblk((size_t)p->L.nf * p->L.nf), p->nHblocks), 256, 0, p->stream>>>(p->d_H, p->d_hblocks, p->nHblocks, d_out, p->N, p->L.nf, p->L.npad, p->d_uperm);
   cudaError_t e = cudaMemcpyAsync(Hout, d_out, U * U * sizeof(double), cudaMemcpyDeviceToHost, p->stream);
   cudaStreamSynchronize(p->stream); cudaFree(d_out);
   if (e != cudaSuccess) return set_err(RCVD_ERR_CUDA, "copy failed: %s", cudaGetErrorString(e));
@@ -1124,7 +1333,7 @@ RCVD_API int32_t rcvd_debug_linear_solve(rcvd_problem* p, const double* S, const
   rc = enqueue_evaluate(p, p->d_x, true, true, p->d_g, SC_COST); if (rc) return rc;
   const int N = p->N, nf = p->L.nf, npad = p->L.npad; const size_t Upad = (size_t)N * npad;
   std::vector<double> hs(Upad, 1.0), hd(Upad, 1.0), hb(Upad, 0.0);
-  for (int f = 0; f < N; ++f) for (int l = 0; l < nf; ++l) { hs[(size_t)f * npad + l] = S[(size_t)f * nf + l]; hd[(size_t)f * npad + l] = D2[(size_t)f * nf + l]; hb[(size_t)f * npad + l] = b[(size_t)f * nf + l]; }
+  for (int f = 0; f < N; ++f) for (int l = 0; l < nf; ++l) { const size_t u = (size_t)p->uperm[f] * nf + l; hs[(size_t)f * npad + l] = S[u]; hd[(size_t)f * npad + l] = D2[u]; hb[(size_t)f * npad + l] = b[u]; }
   CK(cudaMemcpyAsync(p->d_S, hs.data(), Upad * 8, cudaMemcpyHostToDevice, p->stream));
   CK(cudaMemcpyAsync(p->d_D2, hd.data(), Upad * 8, cudaMemcpyHostToDevice, p->stream));
   CK(cudaMemcpyAsync(p->d_gs, hb.data(), Upad * 8, cudaMemcpyHostToDevice, p->stream));
@@ -1133,7 +1342,7 @@ RCVD_API int32_t rcvd_debug_linear_solve(rcvd_problem* p, const double* S, const
   std::vector<double> hy(Upad);
   CK(cudaMemcpyAsync(hy.data(), p->d_y, Upad * 8, cudaMemcpyDeviceToHost, p->stream));
   rc = read_scalars(p); if (rc) return rc;
-  for (int f = 0; f < N; ++f) for (int l = 0; l < nf; ++l) y[(size_t)f * nf + l] = hy[(size_t)f * npad + l];
+  for (int f = 0; f < N; ++f) for (int l = 0; l < nf; ++l) y[(size_t)p->uperm[f] * nf + l] = hy[(size_t)f * npad + l];
   if (*p->h_fail) return set_err(RCVD_ERR_NUMERIC, "factorisation hit a non-positive pivot");
   return RCVD_OK;
 }
@@ -1162,7 +1371,7 @@ RCVD_API int32_t rcvd_time_iteration(rcvd_problem* p, int32_t iters, double radi
     CK(cudaMemsetAsync(p->d_fail, 0, sizeof(int), st));
     CK(cudaEventRecord(p->ev[0], st));
     if ((rc = enqueue_evaluate(p, p->d_x, true, true, p->d_g, SC_COST))) return rc;
-    k_extract_diag<<<nblk(Upad), 256, 0, st>>>(p->d_H, p->d_diagH, N, npad);
+    if (p->nranks <= 1) k_extract_diag<<<nblk(Upad), 256, 0, st>>>(p->d_H, p->d_diagH, N, npad);
     k_jacobi_scale<<<nblk(Upad), 256, 0, st>>>(p->d_diagH, p->d_S, (int)Upad, 1);
     CK(cudaEventRecord(p->ev[1], st));
     k_lm_prepare<<<nblk(Upad), 256, 0, st>>>(p->d_diagH, p->d_S, p->d_g, p->d_lmdiag, p->d_D2, p->d_gs, (int)Upad, 0, radius, 1e-6, 1e32);
@@ -1269,11 +1478,12 @@ RCVD_API int32_t rcvd_debug_linear_residual(rcvd_problem* p, double radius, doub
   CK(cudaMemsetAsync(p->d_scal, 0, SC_N * sizeof(double), st));
   CK(cudaMemsetAsync(p->d_fail, 0, sizeof(int), st));
   if ((rc = enqueue_evaluate(p, p->d_x, true, true, p->d_g, SC_COST))) return rc;
-  k_extract_diag<<<nblk(Upad), 256, 0, st>>>(p->d_H, p->d_diagH, N, npad);
+  if (p->nranks <= 1) k_extract_diag<<<nblk(Upad), 256, 0, st>>>(p->d_H, p->d_diagH, N, npad);
   k_jacobi_scale<<<nblk(Upad), 256, 0, st>>>(p->d_diagH, p->d_S, (int)Upad, 1);
   k_lm_prepare<<<nblk(Upad), 256, 0, st>>>(p->d_diagH, p->d_S, p->d_g, p->d_lmdiag, p->d_D2, p->d_gs, (int)Upad, 0, radius, 1e-6, 1e32);
   if ((rc = factor_solve(p))) return rc;
   if ((rc = enqueue_model_terms(p))) return rc;                      // leaves H (S y) in d_Hy
+  if (p->dist && (rc = allreduce(p, p->d_Hy, Upad))) return rc;      // every rank multiplied only the H blocks it owns
   double* d_out = p->d_scal + 9;                                      // slots 9..12 are unused by the LM loop
   k_lin_residual<<<nblk(Upad), 256, 0, st>>>(p->d_S, p->d_Hy, p->d_D2, p->d_y, p->d_gs, p->d_g, (int)Upad, d_out);
   p->launches += 4;
@@ -1300,12 +1510,29 @@ RCVD_API int32_t rcvd_debug_set_potrf_chain_warp(rcvd_problem* p, int32_t on) { 
 // Test / bench hook: 1 (default) = persistent TMA-fed update kernel (k_update_tma), 0 = round-1 cp.async kernel (k_gemm_nt).
 RCVD_API int32_t rcvd_debug_set_update_kernel(rcvd_problem* p, int32_t tma, int32_t side_items_per_cta) {
   if (!p) return RCVD_ERR_INVALID;
-  p->gemm_tma = tma != 0; p->upd_ipc = side_items_per_cta;
+  p->gemm_tma = (tma & 1) != 0; p->upd_dbg = tma >> 8; p->upd_ipc = side_items_per_cta;   // bits 8+: timing experiments of k_update_tma (results invalid)
   if (p->solve_graph) { cudaGraphExecDestroy(p->solve_graph); p->solve_graph = nullptr; }
   if (p->gemm_tma && !p->tmap_ok) p->structure_ready = false;
   return RCVD_OK;
 }
-RCVD_API int32_t rcvd_debug_set_fast_path(rcvd_problem* p, int32_t on) { if (!p) return RCVD_ERR_INVALID; p->use_fast = on != 0; return RCVD_OK; }
+// Test / bench hook (nranks > 1): 1 (default) = distributed factorisation (owner-computes phase A, reduce-to-owner of H), 0 = round-1 scheme
+// (all-reduce of H, factorisation replicated on every rank).  out (optional): {distributed active, first replicated level, levels}.
+RCVD_API int32_t rcvd_debug_set_distributed(rcvd_problem* p, int32_t on) { if (!p) return RCVD_ERR_INVALID; p->dist_enabled = on != 0; if (p->structure_ready) { int rc_ = save_state(p); if (rc_) return rc_; p->state_dirty = true; } p->structure_ready = false; return RCVD_OK; }
+RCVD_API int32_t rcvd_distribution_info(rcvd_problem* p, int32_t out[4]) {
+  if (!p || !out) return set_err(RCVD_ERR_INVALID, "null argument");
+  SET_DEVICE(p->device);
+  int rc = ensure_ready(p); if (rc) return rc;
+  out[0] = p->dist ? 1 : 0; out[1] = p->LB; out[2] = (int)p->levels.size(); out[3] = p->dist ? p->fa_cnt[p->rank] + p->fb_cnt[p->rank] : p->N;
+  return RCVD_OK;
+}
+// 0: generic kernel, 1 (default): specialised kernels (run path on a bilinear depth grid), 2: specialised kernel without the run path (round 1)
+RCVD_API int32_t rcvd_debug_set_fast_path(rcvd_problem* p, int32_t on) {
+  if (!p) return RCVD_ERR_INVALID;
+  p->use_fast = on != 0;
+  const bool runs = on != 2;
+  if (runs != p->use_runs) { p->use_runs = runs; if (p->structure_ready) { int rc_ = save_state(p); if (rc_) return rc_; } p->structure_ready = false; }
+  return RCVD_OK;
+}
 RCVD_API int32_t rcvd_solve(rcvd_problem* p, const rcvd_solve_options* opt, rcvd_solve_summary* summary) {
   if (!p || !summary) return set_err(RCVD_ERR_INVALID, "null argument");
   SET_DEVICE(p->device);

@@ -345,6 +345,206 @@ __global__ void __launch_bounds__(kTile) k_accumulate_fast(DevProblem p, const d
   block_store_sum(cost, partial + t);
 }
 
+// ---------------------------------------------------------------------------
+// K1 (run path, round 2): bilinear depth grid, the reference's default once coarse-to-fine has left the Global transform.
+// The records of a pair are sorted by (source cell, target cell) when the problem is set up (rcvd_api.cu, device segmented sort), so
+// consecutive constraints share their eight spline nodes.  A run = the constraints of one warp with the same cell pair.  Per run the
+// node rows of the normal equations,
+//       M[node, :] = sum_c  J_node(c)^T [ J_pose(c) | r(c) | J_node(c) ]        (8 x 24: 4 + 4 nodes against 14 pose/focal, r, 8 nodes)
+// are reduced over the run on the fp64 tensor cores (m8n8k4, K = the run's residual rows staged in shared memory) and leave the SM as ONE
+// reduction per entry per run (156 REDs) instead of one per constraint; the 14 x 14 pose/focal block is reduced over the whole
+// 128-constraint tile as before.  matchSeparation 10 (about three constraints per cell pair): ~53 REDs per constraint instead of 157;
+// dense constraints (hundreds per cell pair): ~6.
+// ---------------------------------------------------------------------------
+constexpr int kRunLd = 24;          // [row][col]: 0-13 pose/focal (frame 0, frame 1), 14 r, 15 zero, 16-19 nodes of frame 0, 20-23 nodes of frame 1
+constexpr int kRunSmem = ((3 * kTile + 4) * kRunLd + 4 * 256) * (int)sizeof(double) + kTile * (int)sizeof(unsigned);
+
+__global__ void __launch_bounds__(kTile) k_accumulate_runs(DevProblem p, const double* __restrict__ x, double* __restrict__ H,
+                                                            double* __restrict__ g, double* __restrict__ partial) {
+  extern __shared__ __align__(16) double sm[];
+  double* Js = sm;                                        // [3*kTile + 4][kRunLd]
+  double* Ms = sm + (3 * kTile + 4) * kRunLd;             // [4 warps][16][16]
+  unsigned* skey = reinterpret_cast<unsigned*>(Ms + 4 * 256);
+  const rcvd_config& c = p.cfg; const Layout& L = p.L;
+  const int t = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int pr = p.tile_pair[t];
+  const int f0 = p.pair_frames[2 * pr], f1 = p.pair_frames[2 * pr + 1];
+  const int np = L.npad; const size_t bs = (size_t)np * np;
+  const int enc = p.blk_of[f0 * p.N + f1];
+  double* Hx = H + (size_t)(enc >> 1) * bs;
+  const bool f0rows = enc & 1;
+  double* H0 = H + (size_t)f0 * bs; double* H1 = H + (size_t)f1 * bs;
+  const int gx = c.depth_grid_x;
+  double cost = 0.0;
+  const bool active = tid < p.tile_count[t];
+  unsigned key = 0xffffffffu;
+  {
+    double Jl[60]; double r0 = 0, r1 = 0, r2 = 0; double w0[4] = {0, 0, 0, 0}, w1[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 60; ++i) Jl[i] = 0.0;
+    if (active) {
+      const float* rec = p.records + (size_t)(p.tile_begin[t] + tid) * 6;
+      const double* pf0 = x + (size_t)f0 * L.nf; const double* pf1 = x + (size_t)f1 * L.nf;
+      ObsIn o0{rec[0], rec[1], rec[2]}, o1{rec[3], rec[4], rec[5]};
+      double D0 = (double)o0.depth, D1 = (double)o1.depth;
+      int ix, iy; double rx, ry;
+      cell_coord(o0.ndcx, gx, ix, rx); cell_coord(o0.ndcy, c.depth_grid_y, iy, ry);
+      const int ba = ix + iy * gx;
+      double ox = __dsub_rn(1.0, rx), oy = __dsub_rn(1.0, ry);
+      w0[0] = __dmul_rn(ox, oy); w0[1] = __dmul_rn(rx, oy); w0[2] = __dmul_rn(ox, ry); w0[3] = __dmul_rn(rx, ry);
+      cell_coord(o1.ndcx, gx, ix, rx); cell_coord(o1.ndcy, c.depth_grid_y, iy, ry);
+      const int bb = ix + iy * gx;
+      ox = __dsub_rn(1.0, rx); oy = __dsub_rn(1.0, ry);
+      w1[0] = __dmul_rn(ox, oy); w1[1] = __dmul_rn(rx, oy); w1[2] = __dmul_rn(ox, ry); w1[3] = __dmul_rn(rx, ry);
+      key = ((unsigned)ba << 16) | (unsigned)bb;
+      // GridDepthFunctor::eval: res += (src * s_i) * w_i, in node order
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int na = ba + (q & 1) + (q >> 1) * gx, nb = bb + (q & 1) + (q >> 1) * gx;
+        a0 += (D0 * pf0[L.offD + na]) * w0[q]; a1 += (D1 * pf1[L.offD + nb]) * w1[q];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { w0[q] *= D0; w1[q] *= D1; }          // dD/ds_i = w_i * src
+      D0 = a0; D1 = a1;
+      const double phi0 = (c.intr_opt == RCVD_INTR_PER_FRAME) ? pf0[6] : c.fixed_vfocal;
+      const double phi1 = (c.intr_opt == RCVD_INTR_PER_FRAME) ? pf1[6] : c.fixed_vfocal;
+      const double u[2] = {0.0, 0.0};
+      double r[3];
+      static_scene<true>(c, pf0, phi0, D0, u, pf1, phi1, D1, u, o0, o1, r, Jl);
+      const double s = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+      double rho0, rho1;
+      robust_loss(c, s, rho0, rho1);
+      cost = 0.5 * rho0;
+      const double sc = sqrt(rho1);
+      r0 = r[0] * sc; r1 = r[1] * sc; r2 = r[2] * sc;
+#pragma unroll
+      for (int i = 0; i < 60; ++i) Jl[i] *= sc;
+      if (c.intr_opt != RCVD_INTR_PER_FRAME) { Jl[6] = Jl[26] = Jl[46] = 0.0; Jl[16] = Jl[36] = Jl[56] = 0.0; }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double* row = Js + (size_t)(tid * 3 + i) * kRunLd;
+#pragma unroll
+      for (int q = 0; q < 7; ++q) { row[q] = Jl[i * 20 + q]; row[7 + q] = Jl[i * 20 + 10 + q]; }
+      row[14] = (i == 0) ? r0 : (i == 1 ? r1 : r2);
+      row[15] = 0.0;
+      const double ca = Jl[i * 20 + 7], cb = Jl[i * 20 + 17];            // d r_i / d D0, d r_i / d D1
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { row[16 + q] = ca * w0[q]; row[20 + q] = cb * w1[q]; }
+    }
+    if (tid < 4 * kRunLd) Js[(size_t)3 * kTile * kRunLd + tid] = 0.0;     // four zero rows behind the tile (the K steps of the last run read them)
+    skey[tid] = key;
+  }
+  __syncthreads();
+  const int gq = lane >> 2, tq = lane & 3;
+  // ---- pose / focal block of the whole tile: M = J_P^T [J_P | r] over this warp's 96 residual rows ----
+  {
+    double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+    const double* base = Js + (size_t)warp * 96 * kRunLd;
+#pragma unroll 4
+    for (int k4 = 0; k4 < 24; ++k4) {
+      const double* rowp = base + (size_t)(k4 * 4 + tq) * kRunLd;
+      const double a0 = rowp[gq], a1 = rowp[8 + gq];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) dmma_acc(acc[i][j][0], acc[i][j][1], i ? a1 : a0, j ? a1 : a0);
+    }
+    double* mw = Ms + warp * 256;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { mw[(i * 8 + gq) * 16 + j * 8 + 2 * tq] = acc[i][j][0]; mw[(i * 8 + gq) * 16 + j * 8 + 2 * tq + 1] = acc[i][j][1]; }
+  }
+  // ---- spline-node rows, one run at a time (runs never cross a warp: at most three extra runs per tile) ----
+  {
+    const int c0 = warp * 32 + lane;
+    const unsigned kprev = lane ? skey[c0 - 1] : ~key;
+    const unsigned starts = __ballot_sync(0xffffffffu, key != kprev || lane == 0);
+    unsigned rem = starts;
+    const bool per_frame = c.intr_opt == RCVD_INTR_PER_FRAME;
+    while (rem) {
+      const int s0 = __ffs(rem) - 1; rem &= rem - 1;
+      const int s1 = rem ? __ffs(rem) - 1 : 32;
+      const unsigned rk = skey[warp * 32 + s0];
+      if (rk == 0xffffffffu) break;                        // the padding behind the last constraint of the tile
+      const int row0 = 3 * (warp * 32 + s0), row1 = 3 * (warp * 32 + s1);
+      double acc[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+      for (int rr = row0; rr < row1; rr += 4) {
+        const int row = rr + tq;
+        const double* rowp = Js + (size_t)row * kRunLd;
+        const bool in = row < row1;                                       // the last K step of a run reaches into the next run: masked
+        const double a = in ? rowp[16 + gq] : 0.0;
+#pragma unroll
+        for (int nb = 0; nb < 3; ++nb) dmma_acc(acc[nb][0], acc[nb][1], a, in ? rowp[nb * 8 + gq] : 0.0);
+      }
+      // lane (gq, tq) holds M[node gq][columns nb*8 + 2 tq, + 1]
+      const int ba = (int)(rk >> 16), bb = (int)(rk & 0xffffu);
+      const bool rowA = gq < 4;
+      const int qn = gq & 3;
+      const int ln = L.offD + (rowA ? ba : bb) + (qn & 1) + (qn >> 1) * gx;   // local column of this lane's node
+      double* Hn = rowA ? H0 : H1;                                         // diagonal block of the node's frame
+      const int fn = rowA ? f0 : f1;
+#pragma unroll
+      for (int nb = 0; nb < 3; ++nb)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = nb * 8 + 2 * tq + e;
+          const double v = acc[nb][e];
+          if (col < 14) {
+            const int pc = col < 7 ? col : col - 7;
+            if (pc == 6 && !per_frame) continue;
+            const bool colA = col < 7;
+            if (colA == rowA) red_add(Hn + (size_t)ln * np + pc, v);                         // node row > pose column: lower triangle
+            else if (rowA == f0rows) red_add(Hx + (size_t)ln * np + pc, v);                  // the node's frame is the row side of the cross block
+            else red_add(Hx + (size_t)pc * np + ln, v);
+          } else if (col == 14) {
+            red_add(g + (size_t)fn * np + ln, v);
+          } else if (col >= 16) {
+            const int m = col - 16, qm = m & 3; const bool colNodeA = m < 4;
+            const int lm = L.offD + (colNodeA ? ba : bb) + (qm & 1) + (qm >> 1) * gx;
+            if (colNodeA == rowA) { if (ln >= lm) red_add(Hn + (size_t)ln * np + lm, v); }   // same frame: lower triangle once
+            else if (rowA) {                                                                 // (frame-0 node, frame-1 node): once, from the frame-0 row
+              if (f0rows) red_add(Hx + (size_t)ln * np + lm, v); else red_add(Hx + (size_t)lm * np + ln, v);
+            }
+          }
+        }
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < 256; e += kTile) {
+    const int i = e >> 4, j = e & 15;
+    if (i >= 14 || j >= 15) continue;
+    const double v = Ms[e] + Ms[256 + e] + Ms[512 + e] + Ms[768 + e];
+    const int fi = i < 7 ? f0 : f1, li = i < 7 ? i : i - 7;
+    if (j == 14) { red_add(g + (size_t)fi * np + li, v); continue; }
+    const bool jf0 = j < 7; const int lj = jf0 ? j : j - 7;
+    if ((i < 7) == jf0) { if (li >= lj) red_add((i < 7 ? H0 : H1) + (size_t)li * np + lj, v); }
+    else if (i < 7) { if (f0rows) red_add(Hx + (size_t)li * np + lj, v); else red_add(Hx + (size_t)lj * np + li, v); }
+  }
+  block_store_sum(cost, partial + t);
+}
+
+// Sort key of a record for the run path: (top-left node of the source cell) << 16 | (top-left node of the target cell)
+__global__ void __launch_bounds__(256) k_record_keys(rcvd_config c, const float* __restrict__ records, long long n, unsigned* __restrict__ keys, int* __restrict__ idx) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* rec = records + (size_t)i * 6;
+  int ix, iy; double rx, ry;
+  cell_coord(rec[0], c.depth_grid_x, ix, rx); cell_coord(rec[1], c.depth_grid_y, iy, ry);
+  const unsigned ba = (unsigned)(ix + iy * c.depth_grid_x);
+  cell_coord(rec[3], c.depth_grid_x, ix, rx); cell_coord(rec[4], c.depth_grid_y, iy, ry);
+  keys[i] = (ba << 16) | (unsigned)(ix + iy * c.depth_grid_x);
+  idx[i] = (int)i;
+}
+__global__ void __launch_bounds__(256) k_gather_records(const float* __restrict__ src, const int* __restrict__ idx, long long n, float* __restrict__ dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 6) return;
+  const long long rcd = i / 6; const int e = (int)(i % 6);
+  dst[i] = src[(size_t)idx[rcd] * 6 + e];
+}
+
 // Marks parameters referenced by at least one residual block (the Ceres program's
 // parameter set): used for |x| / |step| norms.  mask has npad stride.
 __global__ void __launch_bounds__(kTile) k_mark_static(DevProblem p, uint8_t* __restrict__ mask) {

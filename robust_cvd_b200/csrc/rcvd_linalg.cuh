@@ -134,36 +134,26 @@ __device__ __forceinline__ void tile_mma_nt(const double* __restrict__ At, const
 // against 5.6 k -- the F2F conversions cost more than the library's MUFU.RSQ64H path; a rotated-row loop form that is not
 // unrolled over j: 17 k cycles.)
 __device__ __forceinline__ void warp_chol16(double* __restrict__ D, double* __restrict__ pinv, int lane, int* __restrict__ fail) {
-  // Pivot-first ordering (round 2): the chain of a right-looking step is  l_{j+1,j} -> a_{j+1,j+1} -> rsqrt -> column scale; the
-  // column-(j+1) update and the next pivot's rsqrt are issued BEFORE the other 14 - j column updates of step j, which then fill
-  // the rsqrt latency instead of delaying it (measured: 5.6 k -> see DESIGN.md cycles per tile).
+  // (round 2: a "pivot-first" ordering -- column j+1 and the next rsqrt issued before the other column updates of step j -- measured
+  // SLOWER, potrf 3.44 -> 3.78 ms per factorisation: the dependent chain shfl, rsqrt, mul, shfl, fma per pivot is the same either way)
   const int i = lane & 15;
   double a[16];
 #pragma unroll
   for (int c = 0; c < 16; ++c) a[c] = (c <= i) ? D[swz(i, c)] : 0.0;
-  double d = __shfl_sync(0xffffffffu, a[0], 0);
-  if (!(d > 0.0) || !isfinite(d)) { if (lane == 0) *fail = 1; d = 1.0; }
-  double pi = rsqrt(d);
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
+    double d = __shfl_sync(0xffffffffu, a[j], j);
+    if (!(d > 0.0) || !isfinite(d)) { if (lane == 0) *fail = 1; d = 1.0; }
+    const double pi = rsqrt(d);
     const double lij = (i == j) ? d * pi : a[j] * pi;
     if (i >= j) a[j] = lij;
     if (lane == 0) pinv[j] = pi;
-    if (j < 15) {
-      // critical column first: a[:, j+1] -= l[:, j] l_{j+1,j}, then the next pivot and its reciprocal square root
-      const double l1 = __shfl_sync(0xffffffffu, lij, j + 1);
-      if (i >= j + 1) a[j + 1] -= lij * l1;
-      double dn = __shfl_sync(0xffffffffu, a[j + 1], j + 1);
-      if (!(dn > 0.0) || !isfinite(dn)) { if (lane == 0) *fail = 1; dn = 1.0; }
-      const double pin = rsqrt(dn);
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        if (c > j + 1) {   // constant trip count so that a[] stays in registers
-          const double lcj = __shfl_sync(0xffffffffu, lij, c);
-          if (i >= c) a[c] -= lij * lcj;
-        }
+    for (int c = 0; c < 16; ++c) {
+      if (c > j) {   // constant trip count so that a[] stays in registers
+        const double lcj = __shfl_sync(0xffffffffu, a[j], c);
+        if (i >= c) a[c] -= lij * lcj;
       }
-      d = dn; pi = pin;
     }
   }
   if (lane < 16) {
@@ -756,8 +746,9 @@ __global__ void __launch_bounds__(256) k_bwd_diag(const double* __restrict__ inv
 // ---------------------------------------------------------------------------
 struct HBlock { int lblk; int r; int c; };   // H list: lblk = destination block in L.  L list: lblk = source block in H (or -1: fill)
 __global__ void __launch_bounds__(256) k_load_factor(const double* __restrict__ H, double* __restrict__ Lb, const HBlock* __restrict__ lb,
-                                                      const double* __restrict__ S, const double* __restrict__ D2, int npad, int nf) {
-  const HBlock b = lb[blockIdx.y];          // blockIdx.y = L block id
+                                                      const double* __restrict__ S, const double* __restrict__ D2, int npad, int nf, const int* __restrict__ blist) {
+  const int bid = blist ? blist[blockIdx.y] : blockIdx.y;   // L block id (blist: the blocks this rank owns)
+  const HBlock b = lb[bid];
   const int e = blockIdx.x * 256 + threadIdx.x;
   if (e >= npad * npad) return;
   const int i = e / npad, j = e % npad;
@@ -773,18 +764,19 @@ __global__ void __launch_bounds__(256) k_load_factor(const double* __restrict__ 
   } else if (b.lblk >= 0 && i < nf && j < nf) {
     v = H[(size_t)b.lblk * bs + e] * S[(size_t)b.r * npad + i] * S[(size_t)b.c * npad + j];
   }
-  Lb[(size_t)blockIdx.y * bs + e] = v;
+  Lb[(size_t)bid * bs + e] = v;
 }
 
 // out += H v over the original block structure (symmetric; diagonal blocks hold the lower triangle).
 // grid: (ceil(npad/8), H blocks), one warp per row i; also accumulates the transposed part.
 __global__ void __launch_bounds__(256) k_spmv_sym(const double* __restrict__ H, const HBlock* __restrict__ hb, const double* __restrict__ v,
-                                                   double* __restrict__ out, int npad) {
-  const HBlock b = hb[blockIdx.y];
+                                                   double* __restrict__ out, int npad, const int* __restrict__ blist) {
+  const int bid = blist ? blist[blockIdx.y] : blockIdx.y;   // H block id (blist: the blocks this rank owns)
+  const HBlock b = hb[bid];
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= npad) return;
-  const double* M = H + (size_t)blockIdx.y * npad * npad + (size_t)row * npad;
+  const double* M = H + (size_t)bid * npad * npad + (size_t)row * npad;
   const double* vc = v + (size_t)b.c * npad;
   const double vr = v[(size_t)b.r * npad + row];
   double s = 0.0;

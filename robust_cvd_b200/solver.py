@@ -173,12 +173,21 @@ class Problem:
         return dict(zip(keys, list(out)))
 
     def set_fast_path(self, on=True):
-        """Test hook: False forces the generic accumulate kernel."""
-        _check(self.L.rcvd_debug_set_fast_path(self.h, C.c_int32(1 if on else 0)))
+        """Test hook: False / 0 forces the generic accumulate kernel, 2 the round-1 specialised kernel without the run path."""
+        _check(self.L.rcvd_debug_set_fast_path(self.h, C.c_int32(int(on))))
 
     def set_update_kernel(self, tma=True, side_items_per_cta=0):
         """Test / bench hook: persistent TMA-fed update kernel (default) or the round-1 cp.async kernel."""
         _check(self.L.rcvd_debug_set_update_kernel(self.h, C.c_int32(1 if tma else 0), C.c_int32(side_items_per_cta)))
+
+    def set_distributed(self, on=True):
+        """Test / bench hook (nranks > 1): distributed factorisation (default) or the round-1 replicated scheme."""
+        _check(self.L.rcvd_debug_set_distributed(self.h, C.c_int32(1 if on else 0)))
+
+    def distribution_info(self):
+        out = (C.c_int32 * 4)()
+        _check(self.L.rcvd_distribution_info(self.h, out))
+        return dict(zip(["distributed", "first_replicated_level", "levels", "frames_owned"], list(out)))
 
     def set_side_slice(self, ctas):
         _check(self.L.rcvd_debug_set_side_slice(self.h, C.c_int32(ctas)))

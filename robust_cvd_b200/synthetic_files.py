@@ -52,27 +52,12 @@ def texture(scene, f):
     return np.ascontiguousarray(img.astype(np.float32))
 
 
-def write_scene(scene, root, depth_tag="depth_midas2", pairs=None, full_size=None, dynamic_masks=None):
-    from .synthetic import hierarchical2_pairs
-    os.makedirs(root, exist_ok=True)
-    for d in ("color_down", "color_full", f"{depth_tag}/depth", "flow", "flow_mask"):
-        os.makedirs(os.path.join(root, d), exist_ok=True)
-    W, H = full_size or (scene.w, scene.h)
-    with open(os.path.join(root, "frames.txt"), "w") as f:
-        f.write(f"{scene.N}\n{W}\n{H}\n" + "".join(f"{i / 30.0:.6f}\n" for i in range(scene.N)))
-    rng = np.random.default_rng(scene.seed + 777)
-    for i in range(scene.N):
-        write_raw(os.path.join(root, "color_down", f"frame_{i:06d}.raw"), texture(scene, i))
-        depth = scene.depth_image(i)
-        write_raw(os.path.join(root, depth_tag, "depth", f"frame_{i:06d}.raw"), (np.float32(1.0) / depth).astype(np.float32))
-        if dynamic_masks is not None:
-            os.makedirs(os.path.join(root, "dynamic_mask"), exist_ok=True)
-            write_png_gray(os.path.join(root, "dynamic_mask", f"frame_{i:06d}.png"), dynamic_masks[i])
-    if pairs is None:
-        pairs = hierarchical2_pairs(scene.N)
+def _write_pairs(scene, root, pairs, seeds):
+    """Flow + mask files of a list of pairs; returns their flow_list rows.  seeds: one rng seed per pair, or a shared Generator."""
     iy, ix = np.mgrid[0:scene.h, 0:scene.w]
-    rows = [["first", "second", "ratio"]]
-    for (a, b) in pairs:
+    rows = []
+    for k, (a, b) in enumerate(pairs):
+        rng = seeds if isinstance(seeds, np.random.Generator) else np.random.default_rng(seeds[k])
         fx1, fy1, ok = scene.flow(a, b, ix.ravel(), iy.ravel(), rng)
         flow = np.stack([fx1 - ix.ravel().astype(np.float32), fy1 - iy.ravel().astype(np.float32)], axis=-1).reshape(scene.h, scene.w, 2).astype(np.float32)
         inside = ok & (fx1 >= 0) & (fx1 <= scene.w - 1) & (fy1 >= 0) & (fy1 <= scene.h - 1)
@@ -80,6 +65,51 @@ def write_scene(scene, root, depth_tag="depth_midas2", pairs=None, full_size=Non
         write_raw(os.path.join(root, "flow", f"flow_{a:06d}_{b:06d}.raw"), flow)
         write_png_gray(os.path.join(root, "flow_mask", f"mask_{a:06d}_{b:06d}.png"), mask)
         rows.append([int(a), int(b), float(mask.mean() / 255.0)])
+    return rows
+
+
+def _write_frames(scene, root, depth_tag, frames, dynamic_masks):
+    for i in frames:
+        write_raw(os.path.join(root, "color_down", f"frame_{i:06d}.raw"), texture(scene, i))
+        depth = scene.depth_image(i)
+        write_raw(os.path.join(root, depth_tag, "depth", f"frame_{i:06d}.raw"), (np.float32(1.0) / depth).astype(np.float32))
+        if dynamic_masks is not None:
+            write_png_gray(os.path.join(root, "dynamic_mask", f"frame_{i:06d}.png"), dynamic_masks[i])
+
+
+def write_scene(scene, root, depth_tag="depth_midas2", pairs=None, full_size=None, dynamic_masks=None, workers=1):
+    """workers > 1: frames and pairs are written by a process pool (flow noise is then seeded per pair instead of drawn from one
+    sequential generator -- a different but equally deterministic realisation)."""
+    from .synthetic import hierarchical2_pairs
+    os.makedirs(root, exist_ok=True)
+    for d in ("color_down", "color_full", f"{depth_tag}/depth", "flow", "flow_mask"):
+        os.makedirs(os.path.join(root, d), exist_ok=True)
+    if dynamic_masks is not None:
+        os.makedirs(os.path.join(root, "dynamic_mask"), exist_ok=True)
+    W, H = full_size or (scene.w, scene.h)
+    with open(os.path.join(root, "frames.txt"), "w") as f:
+        f.write(f"{scene.N}\n{W}\n{H}\n" + "".join(f"{i / 30.0:.6f}\n" for i in range(scene.N)))
+    if pairs is None:
+        pairs = hierarchical2_pairs(scene.N)
+    pairs = list(pairs)
+    if workers <= 1:
+        _write_frames(scene, root, depth_tag, range(scene.N), dynamic_masks)
+        rows = _write_pairs(scene, root, pairs, np.random.default_rng(scene.seed + 777))
+    else:
+        import multiprocessing as mp
+        ctx = mp.get_context("fork")
+        fchunks = [list(range(scene.N))[i::workers] for i in range(workers)]
+        pidx = [list(range(len(pairs)))[i::workers] for i in range(workers)]
+        with ctx.Pool(workers) as pool:
+            jobs = [pool.apply_async(_write_frames, (scene, root, depth_tag, fc, dynamic_masks)) for fc in fchunks if fc]
+            pjobs = [pool.apply_async(_write_pairs, (scene, root, [pairs[k] for k in ix], [scene.seed * 100003 + 777 + k for k in ix])) for ix in pidx if ix]
+            for j in jobs:
+                j.get()
+            got = {}
+            for ix, j in zip([ix for ix in pidx if ix], pjobs):
+                for k, r in zip(ix, j.get()):
+                    got[k] = r
+        rows = [got[k] for k in range(len(pairs))]
     with open(os.path.join(root, "flow_list.json"), "w") as f:
-        json.dump(rows, f)
+        json.dump([["first", "second", "ratio"]] + rows, f)
     return pairs

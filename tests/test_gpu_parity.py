@@ -109,12 +109,35 @@ def test_adaptive_deformation_cost_with_node_weights(cubic):
 def test_fast_kernel_matches_generic(name):
     overrides = dict(helpers.VARIANTS)[name]
     sc, cfg, O, G, x = _both(overrides)
-    Hf = G.normal_matrix_dense(); cf, gf = G.evaluate(True)
-    G.set_fast_path(False)
-    Hg = G.normal_matrix_dense(); cg, gg = G.evaluate(True)
-    assert np.abs(Hf - Hg).max() <= 1e-10 * np.abs(Hg).max()
-    assert np.abs(gf - gg).max() <= 1e-10 * max(1.0, np.abs(gg).max())
-    assert abs(cf - cg) <= 1e-12 * abs(cg)
+    Hf = G.normal_matrix_dense(); cf, gf = G.evaluate(True)      # default: run path on bilinear grids (records sorted by cell pair), else k_accumulate_fast
+    G.set_fast_path(2)
+    Hr = G.normal_matrix_dense(); cr, gr = G.evaluate(True)      # round-1 specialised kernel, unsorted records
+    G.set_fast_path(0)
+    Hg = G.normal_matrix_dense(); cg, gg = G.evaluate(True)      # generic kernel
+    for Hs, cs_, gs_ in ((Hf, cf, gf), (Hr, cr, gr)):
+        assert np.abs(Hs - Hg).max() <= 1e-10 * np.abs(Hg).max()
+        assert np.abs(gs_ - gg).max() <= 1e-10 * max(1.0, np.abs(gg).max())
+        assert abs(cs_ - cg) <= 1e-12 * abs(cg)
+
+
+def test_run_path_dense_and_ragged_runs():
+    """Run path of the accumulate kernel on dense constraints (matchSeparation 0: runs longer than a warp, split at warp and tile
+    boundaries) and on a coarse 3x2 grid (few cell pairs, very long runs) against the generic kernel and the oracle."""
+    from oracle import oracle
+    from robust_cvd_b200 import solver
+    for gx, gy, sep, frames in ((5, 4, 0, 3), (3, 2, 4, 5), (16, 12, 10, 6)):
+        sc, cfg, pairs, offs, rec, med = helpers.make_case(num_frames=frames, w=64, h=48, sep=sep, depth_type=abi.DEPTH_GRID, depth_grid_x=gx, depth_grid_y=gy)
+        off_d, nd = helpers.layout_numbers(cfg)
+        G = solver.Problem(cfg); O = oracle.OracleProblem(cfg)
+        x = helpers.initial_state(sc, cfg, G.stride, off_d, nd)
+        helpers.setup_problem(G, cfg, pairs, offs, rec, med, x); helpers.setup_problem(O, cfg, pairs, offs, rec, med, x)
+        Hf = G.normal_matrix_dense(); cf, gf = G.evaluate(True)
+        Ho = O.normal_matrix_dense(); co, go = O.evaluate(True)
+        assert np.abs(Hf - Ho).max() <= 1e-9 * np.abs(Ho).max()
+        assert np.abs(gf - go).max() <= 1e-9 * max(1.0, np.abs(go).max()) and abs(cf - co) <= 1e-11 * abs(co)
+        G.set_fast_path(0)
+        Hg = G.normal_matrix_dense()
+        assert np.abs(Hf - Hg).max() <= 1e-10 * np.abs(Hg).max()
 
 
 SMOOTH_CASES = [

@@ -195,3 +195,99 @@ def test_static_scene_geometry_against_reference_python_camera_model(loss):
         r2, _ = O.static_jacobian(jac=False)
         p1 = np.stack([fwd[:, 3] * aspect * fwd[:, 5], fwd[:, 4] * fwd[:, 5], -fwd[:, 5]], 1)
         np.testing.assert_allclose(p1 - r2.reshape(-1, 3), g["world"], rtol=0, atol=5e-6)   # r = pw1 - pw0
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------
+# Independent pins of the oracle.  The reference has no tests and Ceres cannot be built here, so these are the
+# checks that do not share a derivation with the oracle: a symbolic restatement of StaticSceneCost (reference lib/PoseOptimizer.cpp:
+# 163-308, Rodrigues rotation as in ceres::AngleAxisRotatePoint) differentiated by sympy, and SciPy's trust-region least squares as an
+# independent minimiser of the same residual vector.
+# ---------------------------------------------------------------------------------------------------------------------------------------
+def _sympy_static_scene(loss_type):
+    import sympy as sp
+    t0 = sp.symbols("t0x t0y t0z"); w0 = sp.symbols("w0x w0y w0z"); t1 = sp.symbols("t1x t1y t1z"); w1 = sp.symbols("w1x w1y w1z")
+    phi0, s0, phi1, s1 = sp.symbols("phi0 s0 phi1 s1")
+    n0x, n0y, d0, n1x, n1y, d1, asp, ws, wd = sp.symbols("n0x n0y d0 n1x n1y d1 asp ws wd")
+
+    def rotate(w, p):                      # ceres::AngleAxisRotatePoint, theta^2 > epsilon branch
+        w = sp.Matrix(w); p = sp.Matrix(p)
+        th = sp.sqrt(w.dot(w)); k = w / th
+        return p * sp.cos(th) + k.cross(p) * sp.sin(th) + k * (k.dot(p)) * (1 - sp.cos(th))
+    D0, D1 = d0 * s0, d1 * s1                                               # Global(Scale) depth transform
+    dir0 = sp.Matrix([n0x * phi0 * asp, n0y * phi0, -1])                     # cameraToWorld
+    X = sp.Matrix(t0) + rotate(w0, dir0) * D0
+    q = rotate([-w1[0], -w1[1], -w1[2]], X - sp.Matrix(t1))                  # worldToCamera
+    depth = -q[2]
+    px, py = q[0] / depth / (phi1 * asp), q[1] / depth / phi1
+    if loss_type == abi.LOSS_REPRO_DISPARITY:
+        rz = (1 / depth - 1 / D1) * wd                                       # both depths > 1e-6 at the test state
+    elif loss_type == abi.LOSS_REPRO_DEPTH_RATIO:
+        rz = (sp.Max(depth, D1) / sp.Min(depth, D1) - 1) * wd
+    else:
+        rz = sp.log(sp.Min(depth, D1) / sp.Max(depth, D1)) * wd
+    r = sp.Matrix([(px - n1x) * ws, (py - n1y) * ws, rz])
+    params = list(t0) + list(w0) + [phi0, s0] + list(t1) + list(w1) + [phi1, s1]
+    consts = [n0x, n0y, d0, n1x, n1y, d1, asp, ws, wd]
+    return sp.lambdify(params + consts, r, "numpy"), sp.lambdify(params + consts, r.jacobian(params), "numpy")
+
+
+@pytest.mark.parametrize("loss_type", [abi.LOSS_REPRO_DISPARITY, abi.LOSS_REPRO_DEPTH_RATIO, abi.LOSS_REPRO_LOG_DEPTH])
+def test_static_scene_cost_matches_sympy_restatement(loss_type):
+    sc, cfg, O, x = _oracle_case(dict(depth_type=abi.DEPTH_GLOBAL, static_loss_type=loss_type), num_frames=4)
+    fr, fJ = _sympy_static_scene(loss_type)
+    r, J = O.static_jacobian(0)
+    sc2, cfg2, pairs, offs, rec, med = helpers.make_case(num_frames=4, depth_type=abi.DEPTH_GLOBAL, static_loss_type=loss_type)
+    X = x.reshape(4, -1)
+    assert X.shape[1] == 8
+    n = 0
+    rng = np.random.default_rng(0)
+    for pi, (a, b) in enumerate(np.asarray(pairs).reshape(-1, 2)):
+        for c in rng.choice(np.arange(offs[pi], offs[pi + 1]), 5, replace=False):
+            k = rec[c].astype(np.float64)
+            args = list(X[a]) + list(X[b]) + [k[0], k[1], k[2], k[3], k[4], k[5], cfg.aspect, cfg.static_spatial_weight, cfg.static_depth_weight]
+            rs = np.asarray(fr(*args), float).ravel(); Js = np.asarray(fJ(*args), float)
+            np.testing.assert_allclose(r[3 * c:3 * c + 3], rs, rtol=1e-10, atol=1e-13)
+            Jo = np.concatenate([J[3 * c:3 * c + 3, a * 8:(a + 1) * 8], J[3 * c:3 * c + 3, b * 8:(b + 1) * 8]], axis=1)
+            assert np.abs(Jo - Js).max() <= 1e-9 * max(1.0, np.abs(Js).max())
+            others = np.delete(J[3 * c:3 * c + 3], np.r_[a * 8:(a + 1) * 8, b * 8:(b + 1) * 8], axis=1)
+            assert not others.any()
+            n += 1
+    assert n >= 30
+
+
+def _relative_geometry(X):
+    """Gauge-invariant summary of a state (N x stride, Global depth): focal, depth scale, pairwise camera distances, relative rotations."""
+    from robust_cvd_b200.synthetic import rodrigues
+    R = [rodrigues(v) for v in X[:, 3:6]]
+    dist = np.array([np.linalg.norm(X[i, :3] - X[j, :3]) for i in range(len(X)) for j in range(i)])
+    rel = np.array([(R[i].T @ R[j]).ravel() for i in range(len(X)) for j in range(i)]).ravel()
+    return np.concatenate([X[:, 6], X[:, 7], dist, rel])
+
+
+def test_lm_optimum_matches_scipy_least_squares():
+    """Non-robust Global-depth problem: the oracle's Ceres-semantics LM and SciPy's trust-region reflective solver (independent code, exact
+    SVD steps, tolerances 1e-14) must reach the same minimum -- same cost, same gauge-invariant geometry (there is no gauge fixing:
+    absolute poses differ by a rigid motion between any two solvers)."""
+    from scipy.optimize import least_squares
+    sc, cfg, O, x = _oracle_case(dict(depth_type=abi.DEPTH_GLOBAL, robust_type=abi.ROBUST_TRIVIAL), num_frames=6)
+
+    def fun(v):
+        O.set_state(v); r, _ = O.static_jacobian(0, jac=False); q, _ = O.regulariser_jacobian(0)
+        return np.concatenate([r, q])
+
+    def jac(v):
+        O.set_state(v); _, J = O.static_jacobian(0); _, K = O.regulariser_jacobian(0)
+        return np.vstack([J, K])
+    x0 = x.reshape(-1).copy()
+    O.set_state(x0); c0 = O.evaluate()
+    assert abs(0.5 * np.sum(fun(x0) ** 2) - c0) <= 1e-12 * c0          # the stacked residual vector IS the oracle's cost
+    res = least_squares(fun, x0, jac=jac, method="trf", tr_solver="exact", xtol=1e-14, ftol=1e-14, gtol=1e-14, max_nfev=400)
+    O.set_state(x0)
+    opt = abi.default_solve_options(max_iterations=400)
+    opt.function_tolerance = 1e-15; opt.parameter_tolerance = 1e-14; opt.gradient_tolerance = 1e-14
+    s = O.solve(opt)
+    xo = O.get_state()
+    assert res.cost < 0.5 * c0
+    assert abs(s.final_cost - res.cost) <= 1e-8 * res.cost, (s.final_cost, res.cost)
+    go, gs = _relative_geometry(xo), _relative_geometry(res.x.reshape(xo.shape))
+    assert np.abs(go - gs).max() <= 1e-4 * np.abs(gs).max(), np.abs(go - gs).max()

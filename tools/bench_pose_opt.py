@@ -1,0 +1,161 @@
+#!/usr/bin/env python3
+"""Metric (ii) of BASELINE.json: pose-optimisation wall-clock, `DepthVideoProcessor.normalizeDepth + optimizePoses` as the reference's
+pose_optimization.py:177-212 calls them, on a 300-frame 384x224 directory on disk -- GPU path through lib_python (constraints from
+rcvd_build_constraints on the flow / mask / colour files, host problem assembly, C-ABI solves, write-back) against the CPU restatement
+(oracle: restated Ceres semantics, NOT Ceres) replaying the same problem arrays with the same iteration cap on the host cores.
+
+  python tools/bench_pose_opt.py [--frames 300] [--max-iterations 12] [--autodiff-iterations 2] [--keep DIR]
+
+Prints one JSON object (bench.py embeds it as "pose_opt_wallclock").  B-analytic = analytic Jacobian + block Cholesky (strongest
+CPU); B-autodiff = Jet<4> passes like DynamicAutoDiffCostFunction<.,4> (the stand-in for the Ceres cost profile, BASELINE.md
+section 3), timed on the final coarse-to-fine step for a few iterations and scaled to that step's iteration count.
+"""
+import argparse
+import json
+import os
+import shutil
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "robust_cvd_b200", "host"))
+
+CV_32FC3 = 21
+
+
+def _open(lp, root):
+    v = lp.DepthVideo(); lp.DepthVideoImporter.importVideo(v, root, False)
+    v.createColorStream("down", "color_down", ".raw", CV_32FC3)
+    v.createDepthStream("depth_midas2", "depth_midas2", [-1, -1])
+    return v
+
+
+def _reset(lp, proc, params):
+    params.op = lp.DepthVideoProcessor.Op.ResetDepthXforms
+    params.depthXformDesc.type = lp.XformType.Depth; params.depthXformDesc.depthType = lp.DepthXformType.Global; params.depthXformDesc.valueXform = lp.ValueXformType.Scale
+    proc.process(params)
+    params.op = lp.DepthVideoProcessor.Op.ResetSpatialXforms
+    params.spatialXformDesc.type = lp.XformType.Spatial; params.spatialXformDesc.spatialType = lp.SpatialXformType.Identity; params.spatialXformDesc.valueXform = lp.ValueXformType.Scale
+    proc.process(params)
+
+
+def _params(lp, v, frames, max_iterations):
+    params = lp.DepthVideoProcessor.Params()
+    params.depthStream = v.numDepthStreams() - 1
+    fs = f"0-{frames - 1}"
+    params.frameRange.fromString(fs); params.poseOptimizer.frameRange.fromString(fs)
+    params.poseOptimizer.maxIterations = max_iterations
+    return params
+
+
+def run(frames=300, w=384, h=224, max_iterations=12, autodiff_iterations=2, keep=None, workers=None, seed=2, skip_cpu=False):
+    import lib_python as lp
+    from robust_cvd_b200 import abi, synthetic, synthetic_files
+    out = {"frames": frames, "image": [w, h], "lm_iteration_cap_per_solve": max_iterations,
+           "what": "DepthVideoProcessor.normalizeDepth + optimizePoses (pose_optimization.py:177-212): Global/Scale reset, 4 coarse-to-fine steps to a 17x10 grid, Cauchy 0.5, PerFrame intrinsics"}
+    root = keep or tempfile.mkdtemp(prefix="rcvd_pose_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        t0 = time.perf_counter()
+        sc = synthetic.Scene(frames, w, h, seed=seed)
+        pairs = synthetic_files.write_scene(sc, root, workers=workers or min(16, os.cpu_count() or 1))
+        out["scene_write_s"] = time.perf_counter() - t0
+        out["pairs"] = len(pairs)
+        # ---------------- GPU path ----------------
+        v = _open(lp, root)
+        fp = lp.FlowConstraintsParams(); fp.frameRange.resolve(v.numFrames(), True); fp.doNotUseCache = True
+        t0 = time.perf_counter()
+        fc = lp.FlowConstraintsCollection(v, fp)              # reads every flow / mask / colour file, GPU constraint builder
+        fc.resetStaticFlag()
+        t_build = time.perf_counter() - t0
+        out["constraints"] = int(sum(len(x[0]) for x in fc._pairs().values()))
+        proc = lp.DepthVideoProcessor(v)
+        params = _params(lp, v, frames, max_iterations)
+        _reset(lp, proc, params)
+        t0 = time.perf_counter()
+        proc.normalizeDepth(params, fc)
+        t_norm = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        proc.optimizePoses(params, fc)
+        t_opt = time.perf_counter() - t0
+        ds = v.depthStream(params.depthStream)
+        out["gpu"] = {"constraint_build_s": t_build, "normalize_depth_s": t_norm, "optimize_poses_s": t_opt, "pose_opt_wallclock_s": t_norm + t_opt,
+                      "final_depth_xform": ds.depthXformDesc().str()}
+        if skip_cpu:
+            return out
+        # ---------------- CPU replay (oracle) of the same solves, step by step ----------------
+        from oracle import oracle
+        oracle.set_threads(oracle.effective_cpus())
+        v2 = _open(lp, root)
+        proc2 = lp.DepthVideoProcessor(v2)
+        p2 = _params(lp, v2, frames, max_iterations)
+        _reset(lp, proc2, p2)
+
+        def replay(d, mode, iters):
+            cfg = abi.Config.from_buffer_copy(d["config"])
+            t = time.perf_counter()
+            O = oracle.OracleProblem(cfg); O.set_jacobian_mode(mode)
+            O.set_frames(d["in_range"], d["median"], d["adaptive"] if d["adaptive"].size else None)
+            O.set_constraints(d["pair_frames"].reshape(-1, 2), d["offsets"], d["records"].reshape(-1, 6))
+            O.set_state(d["state"])
+            s = O.solve(abi.default_solve_options(max_iterations=iters))
+            return time.perf_counter() - t, s
+
+        steps = []
+        opt = lp.DepthVideoPoseOptimizer(v2, p2.depthStream)
+        t0 = time.perf_counter(); d = opt._buildProblem(p2.poseOptimizer, fc, 0.0, True); t_asm = time.perf_counter() - t0
+        tcpu, s = replay(d, 0, max_iterations)
+        steps.append({"step": "normalizeDepth", "cpu_s": tcpu, "assembly_s": t_asm, "iterations": s.iterations, "unknowns_per_frame": int(d["state"].size // frames)})
+        proc2.normalizeDepth(p2, fc)                       # advance the video state with the GPU path (untimed)
+        grids = [(1, 1), (6, 4), (12, 7), (17, 10)]        # ctfLong 17 / ctfShort 10, landscape (lib/PoseOptimizer.cpp:795-802, :858-863)
+        p1 = lp.DepthVideoProcessor.Params(); p1.depthStream = p2.depthStream
+        p1.poseOptimizer = p2.poseOptimizer; p1.poseOptimizer.numSteps = 1; p1.poseOptimizer.coarseToFine = False
+        p1.frameRange.fromString(f"0-{frames - 1}")
+        last = None
+        for step, (gx, gy) in enumerate(grids):
+            if step > 0:
+                sp = lp.DepthVideoProcessor.Params(); sp.depthStream = p2.depthStream
+                sp.depthXformDesc.parse(f"Grid(Scale, Linear, {gx}, {gy}, 1)"); proc2.gridXformSplit(sp)
+            opt = lp.DepthVideoPoseOptimizer(v2, p2.depthStream)
+            # deformation-regulariser schedule of poseOptimization (lib/PoseOptimizer.cpp:834-841)
+            pr = p1.poseOptimizer
+            reg = pr.depthDeformRegFinal
+            if getattr(pr, "graduateDepthDeformReg", False):      # log-linear schedule over the steps
+                reg = float(np.exp(np.log(pr.depthDeformRegInitial) + (np.log(pr.depthDeformRegFinal) - np.log(pr.depthDeformRegInitial)) * step / (len(grids) - 1)))
+            t0 = time.perf_counter(); d = opt._buildProblem(pr, fc, reg, False); t_asm = time.perf_counter() - t0
+            tcpu, s = replay(d, 0, max_iterations)
+            steps.append({"step": f"grid {gx}x{gy}", "cpu_s": tcpu, "assembly_s": t_asm, "iterations": s.iterations, "unknowns_per_frame": int(d["state"].size // frames)})
+            last = (d, s.iterations)
+            proc2.optimizePoses(p1, fc)
+        cpu_total = sum(x["cpu_s"] for x in steps)
+        out["cpu_analytic"] = {"kind": "port (restated Ceres semantics, not Ceres): analytic Jacobian + level-parallel block Cholesky, OpenMP", "cores": oracle.effective_cpus(),
+                               "pose_opt_wallclock_s": cpu_total, "steps": steps}
+        out["speedup_vs_cpu_analytic"] = cpu_total / (t_norm + t_opt)
+        if autodiff_iterations > 0 and last is not None:
+            d, its = last
+            t_ad, s_ad = replay(d, 1, autodiff_iterations)
+            t_an, s_an = replay(d, 0, autodiff_iterations)
+            ratio = t_ad / max(t_an, 1e-9)
+            out["cpu_autodiff"] = {"kind": "port, Jet<4> passes like DynamicAutoDiffCostFunction<.,4> (lib/PoseOptimizer.cpp:1198) + the same block Cholesky",
+                                   "measured": f"final step (17x10 grid), {autodiff_iterations} LM iterations: autodiff {t_ad:.2f} s vs analytic {t_an:.2f} s",
+                                   "autodiff_over_analytic_final_step": ratio,
+                                   "pose_opt_wallclock_s_estimate": cpu_total * ratio, "estimate_note": "analytic total x the final-step ratio (the final step dominates the total)"}
+            out["speedup_vs_cpu_autodiff_estimate"] = cpu_total * ratio / (t_norm + t_opt)
+        return out
+    finally:
+        if not keep:
+            shutil.rmtree(root, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=300)
+    ap.add_argument("--max-iterations", type=int, default=12)
+    ap.add_argument("--autodiff-iterations", type=int, default=2)
+    ap.add_argument("--keep", default=None, help="write the scene here and keep it")
+    ap.add_argument("--skip-cpu", action="store_true")
+    a = ap.parse_args()
+    print(json.dumps(run(frames=a.frames, max_iterations=a.max_iterations, autodiff_iterations=a.autodiff_iterations, keep=a.keep, skip_cpu=a.skip_cpu)))
