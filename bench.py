@@ -250,6 +250,7 @@ def run_ours(args):
         dist.all_gather(allchk, chk)
         if rank == 0:
             Q = solver.Problem(cfg, device=local)
+            Q.set_eval_only(True)        # cost / gradient only: no second copy of the matrices next to the sharded problem
             Q.set_frames(np.ones(cfg.num_frames, np.uint8), med); Q.set_constraints(pairs, offs, rec); Q.set_state(x0)
             c_full, g_full = Q.evaluate(True)
             Q.close()
@@ -283,6 +284,8 @@ def run_ours(args):
         s = P.solve(opt)
         return s, P.get_state()
     e2e = None
+    if world == 1:
+        P.close()          # the e2e calls create their own handle; two resident copies of a large problem (config 4: ~107 GB) do not fit
     if not args.skip_e2e:
         call = e2e_once if world == 1 else e2e_once_multi
         call()
@@ -346,7 +349,6 @@ def run_ours(args):
     if world == 1 and not args.skip_pose_opt:
         # metric (ii): pose-optimisation wall-clock through the reference-facing module (lib_python) on a 300-frame directory on disk
         try:
-            P.close()
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import bench_pose_opt
             line["pose_opt_wallclock"] = bench_pose_opt.run(frames=args.pose_opt_frames, max_iterations=args.pose_opt_iterations, autodiff_iterations=1, skip_cpu=args.skip_cpu)
@@ -382,7 +384,13 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_ours(args)
+        try:
+            run_ours(args)
+        except BaseException:
+            import traceback
+            traceback.print_exc()
+            sys.stderr.flush()
+            os._exit(1)          # a rank that failed must not linger in a collective: the launcher then tears the job down at once
 
 
 if __name__ == "__main__":

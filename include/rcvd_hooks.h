@@ -28,6 +28,8 @@ int32_t rcvd_debug_linear_residual(rcvd_problem* p, double radius, double out[6]
  * substitution; [6] = update-GEMM launches, [7] = their algorithmic flops.  reps > 0: serialised on one stream;
  * reps < 0: two-stream overlap kept, main-stream view. */
 int32_t rcvd_debug_profile_linear(rcvd_problem* p, int32_t reps, double out_ms[8]);
+/* per-level view of the last rcvd_debug_profile_linear call: out[level][6] ms of {load, potrf, trinv, trsm, update, substitution} */
+int32_t rcvd_debug_level_profile(rcvd_problem* p, double* out, int32_t max_levels);
 /* fp64 tensor-core (DMMA) peak of the device in TFLOP/s, measured live */
 int32_t rcvd_debug_fp64_tensor_peak(int32_t device, double* tflops);
 
@@ -38,6 +40,7 @@ int32_t rcvd_debug_set_trsm_ll(rcvd_problem* p, int32_t on);          /* (1) lef
 int32_t rcvd_debug_set_order_slack(rcvd_problem* p, int32_t slack);   /* (4) multiple-elimination degree slack; -1 greedy */
 int32_t rcvd_debug_set_trim_gemm(rcvd_problem* p, int32_t on);        /* (1) update GEMMs skip the zero padding beyond ceil8(unknowns) */
 int32_t rcvd_debug_set_potrf_chain_warp(rcvd_problem* p, int32_t on); /* (1) warp 0 of k_potrf_smem is dedicated to the pivot chain */
+int32_t rcvd_debug_set_eval_only(rcvd_problem* p, int32_t on);        /* (0) cost / gradient evaluations only: no matrix storage (the whole-problem check of a multi-GPU bench) */
 int32_t rcvd_debug_set_distributed(rcvd_problem* p, int32_t on);      /* (1) nranks > 1: distributed factorisation; 0 = all-reduce H + replicated factorisation */
 int32_t rcvd_distribution_info(rcvd_problem* p, int32_t out[4]);       /* {distributed, first replicated level, levels, frames owned by this rank} */
 int32_t rcvd_debug_set_side_slice(rcvd_problem* p, int32_t ctas);     /* (0) grid cap of one overlapped update launch */

@@ -226,7 +226,7 @@ struct rcvd_problem {
   std::vector<HBlock> hblocks;
   // schedule
   std::vector<Level> levels; int *d_lvl_frames = nullptr; GemmTask *d_trsm_tasks = nullptr, *d_upd_tasks = nullptr; int2 *d_trsm_pairs = nullptr, *d_upd_pairs = nullptr;
-  SolveTask *d_fwd_tasks = nullptr, *d_col_tasks = nullptr; int* d_col_ptr = nullptr; TrsmTask* d_trsm_ll = nullptr; bool use_trsm_ll = false;
+  SolveTask *d_fwd_tasks = nullptr, *d_col_tasks = nullptr; int* d_col_ptr = nullptr; TrsmTask* d_trsm_ll = nullptr; bool use_trsm_ll = false, trsm_deep = true;
   cudaGraphExec_t solve_graph = nullptr;
   bool structure_ready = false, constraints_set = false, frames_set = false;
   // multi GPU
@@ -240,12 +240,14 @@ struct rcvd_problem {
   // kernel-class profiling (rcvd_debug_profile_linear): when set, enqueue_factor_solve records one event per launch
   std::vector<std::pair<int, cudaEvent_t>>* prof = nullptr;
   // distributed factorisation (nranks > 1): ownership, internal frame numbering, broadcast / reduce segments
+  bool eval_only = false;   // test / bench hook: only rcvd_evaluate is used (no H, no factor storage)
   bool use_runs = true, records_sorted = false;   // run path of the accumulate kernel (bilinear depth grid): records sorted by cell pair
   bool dist_enabled = true, dist = false, identity_perm = true, graph_warm = false, force_full_H = false; int LB = 0;
   std::vector<int> uperm, iperm, fa_off, fa_cnt, fb_off, fb_cnt, tseg, bseg, hseg;   // *_off/_cnt: per-owner frame ranges (phase A / B); segs: (first, count) pairs
   int *d_lvl_own = nullptr, *d_own_lblocks = nullptr, *d_own_hblocks = nullptr, *d_uperm = nullptr; int n_own_l = 0, n_own_h = 0;
   // TMA-fed persistent update kernel (rcvd_update.cuh)
-  UpdItem* d_upd_items = nullptr; CUtensorMap tmapT; bool gemm_tma = true, tmap_ok = false; int upd_rb = 0, upd_neff = 0, num_sms = 148, upd_ipc = 0, upd_dbg = 0;
+  UpdItem* d_upd_items = nullptr; CUtensorMap tmapT; bool gemm_tma = true, tmap_ok = false; int upd_rb = 0, upd_neff = 0, num_sms = 148, upd_ipc = 0, upd_dbg = 0, upd_team_items = 1;   // upd_team_items: launches of <= that many items per SM take the two-team shape
+  std::vector<double> level_ms;   // last rcvd_debug_profile_linear: per level x kernel class
   double upd_flops = 0.0;   // algorithmic flops of the update GEMMs of one factorisation (2 nf^3 per product, nf^2 (nf+1) on symmetric targets)
   rcvd_problem() {}
 };
@@ -432,10 +434,10 @@ static int build_structure(rcvd_problem* p) {
   std::vector<int> lvl_frames, lvl_own; std::vector<GemmTask> trsm_tasks, upd_tasks; std::vector<int2> trsm_pairs, upd_pairs;
   std::vector<SolveTask> fwd_tasks, col_tasks; std::vector<int> col_ptr(N + 1, 0); std::vector<TrsmTask> trsm_ll;
   std::vector<UpdItem> upd_items;
-  // tile cut of the update targets: as few tiles of <= kUpdMaxTile rows as cover the unknowns (rounded to 8), equal sizes
+  // tile cut of the update targets: kUpdMaxTile-row tiles over the unknowns (rounded to 8)
   const int upd_neff = std::min(npad, (L.nf + 7) / 8 * 8);
   const int upd_nt = (upd_neff + kUpdMaxTile - 1) / kUpdMaxTile;
-  const int upd_tile = ((upd_neff + upd_nt - 1) / upd_nt + 7) / 8 * 8;
+  const int upd_tile = std::min(kUpdMaxTile, upd_neff);          // 80-row tiles (balanced 5 x 5 units per warp), the remainder last
   p->upd_rb = upd_tile; p->upd_neff = upd_neff;
   p->levels.clear();
   for (int l = 0; l < nl; ++l) {
@@ -580,8 +582,11 @@ static int build_structure(rcvd_problem* p) {
   const RegCounts rcn = reg_counts(p->cfg, L, N, p->nscale);
   p->npartial = p->num_tiles + (rcn.total + 127) / 128 + p->num_trip_tiles + 1;
   DA(p->d_partial, (size_t)p->npartial);
-  DA(p->d_H, (size_t)p->nHblocks * bs); DA(p->d_Lb, (size_t)(N + nLoff) * bs); DA(p->d_T, (size_t)std::max(nLoff, 1) * bs);
-  DA(p->d_invL, (size_t)N * bs); DA(p->d_invT, (size_t)N * npad * 16);
+  if (p->eval_only) { DA(p->d_H, 1); DA(p->d_Lb, 1); DA(p->d_T, 1); DA(p->d_invL, 1); DA(p->d_invT, 1); }   // cost / gradient evaluations only: no matrices
+  else {
+    DA(p->d_H, (size_t)p->nHblocks * bs); DA(p->d_Lb, (size_t)(N + nLoff) * bs); DA(p->d_T, (size_t)std::max(nLoff, 1) * bs);
+    DA(p->d_invL, (size_t)N * bs); DA(p->d_invT, (size_t)N * npad * 16);
+  }
 #undef DA
   {
     // 2-D TMA view of the T buffer (off-diagonal factor blocks X_rk, row-major): inner = k, outer = block * npad + row, box [rb][16], 128-B swizzle
@@ -600,7 +605,7 @@ static int build_structure(rcvd_problem* p) {
       p->tmap_ok = (r == CUDA_SUCCESS);
     }
     cudaGetLastError();
-    if (p->tmap_ok) CK(cudaFuncSetAttribute(k_update_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem_bytes(p->upd_rb)));
+    if (p->tmap_ok) { CK(cudaFuncSetAttribute(k_update_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem_bytes(p->upd_rb, 1))); CK(cudaFuncSetAttribute(k_update_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem_bytes(p->upd_rb, 2))); }
     else if (p->gemm_tma) return set_err(RCVD_ERR_CUDA, "cuTensorMapEncodeTiled unavailable or failed: the TMA update kernel cannot run");
   }
   CK(cudaMallocHost((void**)&p->h_scal, (SC_N + 2) * sizeof(double)));
@@ -629,7 +634,7 @@ static int build_structure(rcvd_problem* p) {
   CK(cudaFuncSetAttribute(k_accumulate_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem));
   CK(cudaFuncSetAttribute(k_accumulate_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, kRunSmem));
   p->use_trsm_ll = p->allow_trsm_ll && trsm_ll_smem_bytes(npad) <= 220 * 1024;
-  if (p->use_trsm_ll) CK(cudaFuncSetAttribute(k_trsm_ll, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_ll_smem_bytes(npad)));
+  if (p->use_trsm_ll) { CK(cudaFuncSetAttribute(k_trsm_ll<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_ll_smem_bytes(npad, 2))); if (trsm_ll_smem_bytes(npad, 4) <= 220 * 1024) CK(cudaFuncSetAttribute(k_trsm_ll<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_ll_smem_bytes(npad, 4))); }
   if (potrf_smem_bytes(npad) <= 220 * 1024) CK(cudaFuncSetAttribute(k_potrf_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_smem_bytes(npad)));
   CK(cudaStreamSynchronize(p->stream));
   p->structure_ready = true;
@@ -666,9 +671,10 @@ static int enqueue_factor_solve(rcvd_problem* p) {
   const int nL = N + p->nLoff;
   const int tiles = (npad + 63) / 64;
   enum { P_LOAD = 0, P_POTRF, P_TRINV, P_TRSM, P_GEMM, P_SOLVE };
+  int prof_level = 0;
   auto mark = [&](int cls) {   // profiling mode only (single stream, not captured)
     if (!p->prof) return;
-    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); p->prof->push_back({cls, e});
+    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); p->prof->push_back({cls < 0 ? cls : (cls | (prof_level << 8)), e});
   };
   const int neff = p->trim_gemm ? std::min(npad, (L.nf + 7) / 8 * 8) : npad;
   auto gemm = [&](cudaStream_t cs, int ntasks, double* dstp, const double* A, const double* B, const GemmTask* tasks, const int2* prs, double alpha, double beta) {
@@ -695,7 +701,7 @@ static int enqueue_factor_solve(rcvd_problem* p) {
     return grouped(p, p->d_Lb, bsz, tr, true);
   };
   for (size_t li = 0; li < p->levels.size(); ++li) {
-    const Level& lv = p->levels[li];
+    const Level& lv = p->levels[li]; prof_level = (int)li;
     if (p->dist && (int)li == p->LB) { int rc = phase_boundary(); if (rc) return rc; }
     const int* lframes = p->d_lvl_own + lv.own_off; const int nfr = lv.nown;      // the frames this rank factors at this level
     if (nfr > 0) {
@@ -719,7 +725,14 @@ static int enqueue_factor_solve(rcvd_problem* p) {
       if (p->overlap) { CK(cudaEventRecord(p->ev_fork, st)); CK(cudaStreamWaitEvent(side, p->ev_fork, 0)); is = side; side_used = true; }
       k_trinv<<<dim3(npad / 16, nfr), 256, (npad * 16 + 16 * (npad + 1)) * sizeof(double), is>>>(p->d_Lb, p->d_invT, p->d_invL, lframes, npad);
       p->launches += 1; mark(P_TRINV);
-      if (lv.ntrsm > 0) { k_trsm_ll<<<dim3((npad + kTrsmStrip - 1) / kTrsmStrip, lv.ntrsm), 128, trsm_ll_smem_bytes(npad), st>>>(p->d_T, p->d_Lb, p->d_invT, p->d_trsm_ll + lv.trsm_off, npad); p->launches++; mark(P_TRSM); }
+      if (lv.ntrsm > 0) {
+        const int strips = (npad + kTrsmStrip - 1) / kTrsmStrip;
+        if (p->trsm_deep && strips * lv.ntrsm <= p->num_sms && trsm_ll_smem_bytes(npad, 4) <= 220 * 1024)   // a single wave: deep panel prefetch, one CTA per SM
+          k_trsm_ll<4><<<dim3(strips, lv.ntrsm), 128, trsm_ll_smem_bytes(npad, 4), st>>>(p->d_T, p->d_Lb, p->d_invT, p->d_trsm_ll + lv.trsm_off, npad);
+        else
+          k_trsm_ll<2><<<dim3(strips, lv.ntrsm), 128, trsm_ll_smem_bytes(npad, 2), st>>>(p->d_T, p->d_Lb, p->d_invT, p->d_trsm_ll + lv.trsm_off, npad);
+        p->launches++; mark(P_TRSM);
+      }
     } else {
       k_trinv<<<dim3(npad / 16, nfr), 256, (npad * 16 + 16 * (npad + 1)) * sizeof(double), st>>>(p->d_Lb, p->d_invT, p->d_invL, lframes, npad);
       p->launches += 1; mark(P_TRINV);
@@ -737,9 +750,14 @@ static int enqueue_factor_solve(rcvd_problem* p) {
     }
     if (side_pending) { CK(cudaStreamWaitEvent(st, p->ev_join, 0)); side_pending = false; }   // U2(l-1) before U1(l)
     auto update = [&](cudaStream_t cs, int off, int n, bool side_launch) {   // persistent TMA-fed update kernel
-      int grid = std::min(n, 2 * p->num_sms);
-      if (side_launch && p->upd_ipc > 0) grid = std::max(grid, (n + p->upd_ipc - 1) / p->upd_ipc);
-      k_update_tma<<<grid, kUpdThreads, upd_smem_bytes(p->upd_rb), cs>>>(p->tmapT, p->d_Lb, p->d_upd_items + off, n, p->d_upd_pairs, npad, p->upd_neff, p->upd_rb, p->upd_dbg);
+      (void)side_launch;
+      if (n <= p->num_sms * p->upd_team_items) {   // few items: two DMMA teams per tile, one CTA per SM
+        k_update_tma<2><<<std::min(n, p->num_sms), UpdShape<2>::threads, upd_smem_bytes(p->upd_rb, 2), cs>>>(p->tmapT, p->d_Lb, p->d_upd_items + off, n, p->d_upd_pairs, npad, p->upd_neff, p->upd_rb, p->upd_dbg);
+      } else {
+        int grid = std::min(n, 2 * p->num_sms);
+        if (p->upd_ipc > 0) grid = std::max(grid, (n + p->upd_ipc - 1) / p->upd_ipc);
+        k_update_tma<1><<<grid, UpdShape<1>::threads, upd_smem_bytes(p->upd_rb, 1), cs>>>(p->tmapT, p->d_Lb, p->d_upd_items + off, n, p->d_upd_pairs, npad, p->upd_neff, p->upd_rb, p->upd_dbg);
+      }
     };
     if (p->gemm_tma) {
       if (lv.nit > 0) { update(st, lv.it_off, lv.nit, false); p->launches++; mark(P_GEMM); }
@@ -812,6 +830,7 @@ static int factor_solve(rcvd_problem* p) {
 
 // Cost (-> d_scal[slot]) at state x; optionally gradient (gout, npad stride) and H.
 static int enqueue_evaluate(rcvd_problem* p, const double* x, bool wantG, bool wantH, double* gout, int slot) {
+  if (wantH && p->eval_only) return set_err(RCVD_ERR_INVALID, "this handle was set to evaluation-only (rcvd_debug_set_eval_only): no normal matrix");
   const Layout& L = p->L; const int N = p->N, npad = L.npad; cudaStream_t st = p->stream;
   const size_t bs = (size_t)npad * npad, Upad = (size_t)N * npad;
   DevProblem d = dev_problem(p);
@@ -1400,6 +1419,7 @@ RCVD_API int32_t rcvd_debug_profile_linear(rcvd_problem* p, int32_t reps, double
   const bool ov = p->overlap; if (!keep_overlap) p->overlap = false;
   for (int i = 0; i < 8; ++i) out_ms[i] = 0.0;
   std::vector<std::pair<int, cudaEvent_t>> evs;
+  p->level_ms.assign(p->levels.size() * 6, 0.0);
   for (int r = -1; r < reps; ++r) {
     CK(cudaMemsetAsync(p->d_fail, 0, sizeof(int), p->stream));
     evs.clear(); p->prof = &evs;
@@ -1409,8 +1429,10 @@ RCVD_API int32_t rcvd_debug_profile_linear(rcvd_problem* p, int32_t reps, double
     double ngemm = 0;
     for (size_t i = 1; i < evs.size(); ++i) {
       float ms = 0; cudaEventElapsedTime(&ms, evs[i - 1].second, evs[i].second);
-      if (r >= 0 && evs[i].first >= 0 && evs[i].first < 6) out_ms[evs[i].first] += ms;
-      if (evs[i].first == 4) ngemm += 1;
+      const int cls = evs[i].first < 0 ? -1 : (evs[i].first & 0xff), lvl = evs[i].first < 0 ? 0 : (evs[i].first >> 8);
+      if (r >= 0 && cls >= 0 && cls < 6) out_ms[cls] += ms;
+      if (cls == 4) ngemm += 1;
+      if (r == reps - 1 && cls >= 0 && cls < 6 && p->level_ms.size() >= (size_t)(lvl + 1) * 6) p->level_ms[(size_t)lvl * 6 + cls] += ms;
     }
     for (auto& e : evs) cudaEventDestroy(e.second);
     out_ms[6] = ngemm;
@@ -1493,6 +1515,13 @@ RCVD_API int32_t rcvd_debug_linear_residual(rcvd_problem* p, double radius, doub
   out[3] = std::sqrt(p->h_scal[11]); out[4] = std::sqrt(p->h_scal[12]); out[5] = (double)*p->h_fail;
   return RCVD_OK;
 }
+// per-level view of the last rcvd_debug_profile_linear call: out[level][6] = ms of {load, potrf, trinv, trsm, update, substitution}; returns levels
+RCVD_API int32_t rcvd_debug_level_profile(rcvd_problem* p, double* out, int32_t max_levels) {
+  if (!p || !out) return -1;
+  const int n = std::min<int>(max_levels, (int)(p->level_ms.size() / 6));
+  for (int i = 0; i < n * 6; ++i) out[i] = p->level_ms[i];
+  return n;
+}
 RCVD_API int64_t rcvd_launch_count(rcvd_problem* p) { return p ? p->launches : 0; }
 // Test hook: 0 forces the generic accumulate kernel, 1 (default) allows the specialised one.
 // Test / bench hook: elimination-order variant (-1 greedy minimum degree, >= 0 multiple elimination with that degree slack).
@@ -1500,7 +1529,7 @@ RCVD_API int32_t rcvd_debug_set_order_slack(rcvd_problem* p, int32_t slack) { if
 // Test / bench hook: 0 = single-stream factorisation graph, 1 (default) = overlap non-critical updates on a second stream.
 RCVD_API int32_t rcvd_debug_set_overlap(rcvd_problem* p, int32_t on) { if (!p) return RCVD_ERR_INVALID; p->overlap = on != 0; if (p->solve_graph) { cudaGraphExecDestroy(p->solve_graph); p->solve_graph = nullptr; } return RCVD_OK; }
 // Test / bench hook: 0 = explicit inverse + GEMM for the off-diagonal solves, 1 (default) = left-looking tensor-core TRSM.
-RCVD_API int32_t rcvd_debug_set_trsm_ll(rcvd_problem* p, int32_t on) { if (!p) return RCVD_ERR_INVALID; p->allow_trsm_ll = on != 0; p->structure_ready = false; return RCVD_OK; }
+RCVD_API int32_t rcvd_debug_set_trsm_ll(rcvd_problem* p, int32_t on) { if (!p) return RCVD_ERR_INVALID; p->allow_trsm_ll = (on & 1) != 0; p->trsm_deep = !(on & 2); p->structure_ready = false; return RCVD_OK; }   // bit 0: left-looking TRSM; bit 1: no deep panel prefetch on single-wave launches
 // Test / bench hook: grid-size cap (CTAs) of one overlapped update launch on the side stream; 0 = unsliced.
 RCVD_API int32_t rcvd_debug_set_side_slice(rcvd_problem* p, int32_t ctas) { if (!p) return RCVD_ERR_INVALID; p->side_slice = ctas; if (p->solve_graph) { cudaGraphExecDestroy(p->solve_graph); p->solve_graph = nullptr; } return RCVD_OK; }
 // Test / bench hook: 0 = update GEMMs over the padded size, 1 (default) = trimmed to the unknowns rounded to 8.
@@ -1510,13 +1539,15 @@ RCVD_API int32_t rcvd_debug_set_potrf_chain_warp(rcvd_problem* p, int32_t on) { 
 // Test / bench hook: 1 (default) = persistent TMA-fed update kernel (k_update_tma), 0 = round-1 cp.async kernel (k_gemm_nt).
 RCVD_API int32_t rcvd_debug_set_update_kernel(rcvd_problem* p, int32_t tma, int32_t side_items_per_cta) {
   if (!p) return RCVD_ERR_INVALID;
-  p->gemm_tma = (tma & 1) != 0; p->upd_dbg = tma >> 8; p->upd_ipc = side_items_per_cta;   // bits 8+: timing experiments of k_update_tma (results invalid)
+  p->gemm_tma = (tma & 1) != 0; p->upd_dbg = (tma >> 8) & 0xff; p->upd_team_items = (tma >> 16) ? (tma >> 16) - 1 : 1; p->upd_ipc = side_items_per_cta;   // bits 16+: (items per SM up to which the two-team shape is used) + 1   // bits 8+: timing experiments of k_update_tma (results invalid)
   if (p->solve_graph) { cudaGraphExecDestroy(p->solve_graph); p->solve_graph = nullptr; }
   if (p->gemm_tma && !p->tmap_ok) p->structure_ready = false;
   return RCVD_OK;
 }
 // Test / bench hook (nranks > 1): 1 (default) = distributed factorisation (owner-computes phase A, reduce-to-owner of H), 0 = round-1 scheme
 // (all-reduce of H, factorisation replicated on every rank).  out (optional): {distributed active, first replicated level, levels}.
+// Test / bench hook: 1 = the handle will only evaluate cost / gradient (rcvd_evaluate): no normal matrix, no factor storage is allocated
+RCVD_API int32_t rcvd_debug_set_eval_only(rcvd_problem* p, int32_t on) { if (!p) return RCVD_ERR_INVALID; p->eval_only = on != 0; p->structure_ready = false; return RCVD_OK; }
 RCVD_API int32_t rcvd_debug_set_distributed(rcvd_problem* p, int32_t on) { if (!p) return RCVD_ERR_INVALID; p->dist_enabled = on != 0; if (p->structure_ready) { int rc_ = save_state(p); if (rc_) return rc_; p->state_dirty = true; } p->structure_ready = false; return RCVD_OK; }
 RCVD_API int32_t rcvd_distribution_info(rcvd_problem* p, int32_t out[4]) {
   if (!p || !out) return set_err(RCVD_ERR_INVALID, "null argument");

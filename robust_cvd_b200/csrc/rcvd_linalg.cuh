@@ -505,15 +505,20 @@ struct TrsmTask { int dst; int src; int kframe; };   // T index, L block id, col
 // launch that does not fill the machine (the dense tail), and two co-resident CTAs hide each other's staging waits elsewhere.
 constexpr int kTrsmRW = 8;
 constexpr int kTrsmStrip = 4 * kTrsmRW;
-__host__ __device__ inline size_t trsm_ll_smem_bytes(int npad) { return ((size_t)kTrsmStrip * (npad + 4) + 2 * 16 * (size_t)(npad + 4) + 2 * 16 * 20) * sizeof(double); }
+// The L row panels are prefetched AHEAD steps ahead through a ring.  AHEAD = 2 (108 KB at npad 208, two CTAs per SM) for launches that
+// fill the machine; AHEAD = 4 (169 KB, one CTA per SM) for the narrow levels, where a launch is a single wave and every step of the
+// chain otherwise waits for its panel to come back from L2 (measured in round 2: all launches at AHEAD = 4 made the wide levels slower,
+// trsm 2.03 -> 2.72 ms per factorisation, because occupancy halves where throughput counts).
+__host__ __device__ inline size_t trsm_ll_smem_bytes(int npad, int ahead = 2) { return ((size_t)kTrsmStrip * (npad + 4) + ahead * 16 * (size_t)(npad + 4) + ahead * 16 * 20) * sizeof(double); }
 
+template <int kTrsmAhead>
 __global__ void __launch_bounds__(128) k_trsm_ll(double* __restrict__ T, const double* __restrict__ Lb, const double* __restrict__ invT,
                                                   const TrsmTask* __restrict__ tasks, int npad) {
   extern __shared__ __align__(16) double smx[];
   const int ld = npad + 4;                       // ld = 4 (mod 16): conflict-free DMMA fragment loads
   double* Xs = smx;                              // [kTrsmStrip][ld]
-  double* Ls = smx + (size_t)kTrsmStrip * ld;            // [2][16][ld]   L[jt*16 .. +15][0 .. jt*16)
-  double* Ds = Ls + (size_t)2 * 16 * ld;         // [2][16][20]   Di_jt
+  double* Ls = smx + (size_t)kTrsmStrip * ld;    // [kTrsmAhead][16][ld]   L[jt*16 .. +15][0 .. jt*16)
+  double* Ds = Ls + (size_t)kTrsmAhead * 16 * ld;   // [kTrsmAhead][16][20]   Di_jt
   const TrsmTask task = tasks[blockIdx.y];
   const int m0 = blockIdx.x * kTrsmStrip;
   const size_t bs = (size_t)npad * npad;
@@ -530,20 +535,23 @@ __global__ void __launch_bounds__(128) k_trsm_ll(double* __restrict__ T, const d
     const bool v = r < rows;
     cp_async16(&Xs[(size_t)r * ld + c], A + (size_t)(v ? m0 + r : 0) * npad + c, v);
   }
-  auto stage = [&](int jt) {   // L row panel (columns [0, jt*16)) and Di of step jt into buffer jt & 1
-    double* ls = Ls + (size_t)(jt & 1) * 16 * ld; double* dsm = Ds + (jt & 1) * 320;
-    const int kw = jt * 16;
-    for (int e = tid; e < 16 * (kw / 2); e += 128) { const int r = e / (kw / 2), c = (e % (kw / 2)) * 2; cp_async16(&ls[(size_t)r * ld + c], Lk + (size_t)(jt * 16 + r) * npad + c, true); }
-    { const int r = tid >> 3, c = (tid & 7) * 2; cp_async16(&dsm[r * 20 + c], iT + (size_t)jt * 256 + r * 16 + c, true); }
+  auto stage = [&](int jt) {   // L row panel (columns [0, jt*16)) and Di of step jt into ring slot jt % kTrsmAhead; always one commit group (may be empty)
+    if (jt < nt) {
+      double* ls = Ls + (size_t)(jt % kTrsmAhead) * 16 * ld; double* dsm = Ds + (jt % kTrsmAhead) * 320;
+      const int kw = jt * 16;
+      for (int e = tid; e < 16 * (kw / 2); e += 128) { const int r = e / (kw / 2), c = (e % (kw / 2)) * 2; cp_async16(&ls[(size_t)r * ld + c], Lk + (size_t)(jt * 16 + r) * npad + c, true); }
+      { const int r = tid >> 3, c = (tid & 7) * 2; cp_async16(&dsm[r * 20 + c], iT + (size_t)jt * 256 + r * 16 + c, true); }
+    }
     cp_async_commit();
   };
-  stage(0);
+#pragma unroll
+  for (int q = 0; q < kTrsmAhead; ++q) stage(q);         // group 0 also carries the A strip
   constexpr int NI = kTrsmRW / 8;                 // m8 tiles per warp
   const int wr = warp * kTrsmRW;                  // this warp's rows inside the strip
   for (int jt = 0; jt < nt; ++jt) {
-    if (jt + 1 < nt) { stage(jt + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    cp_async_wait<kTrsmAhead - 1>();              // groups complete in order: panel jt has landed, up to kTrsmAhead - 1 later ones may be in flight
     __syncthreads();
-    const double* ls = Ls + (size_t)(jt & 1) * 16 * ld; const double* dsm = Ds + (jt & 1) * 320;
+    const double* ls = Ls + (size_t)(jt % kTrsmAhead) * 16 * ld; const double* dsm = Ds + (jt % kTrsmAhead) * 320;
     double acc[NI][2][2];
 #pragma unroll
     for (int i = 0; i < NI; ++i) { acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0; }
@@ -592,7 +600,8 @@ __global__ void __launch_bounds__(128) k_trsm_ll(double* __restrict__ T, const d
         *reinterpret_cast<double2*>(&Xs[(size_t)r * ld + cidx]) = v;
         if (r < rows) *reinterpret_cast<double2*>(&X[(size_t)(m0 + r) * npad + cidx]) = v;
       }
-    __syncthreads();   // X[:, jt] visible to... (each warp only reads its own rows; the barrier protects the L/Di double buffer)
+    __syncthreads();   // every warp is done with ring slot jt % kTrsmAhead before it is refilled
+    stage(jt + kTrsmAhead);
   }
 }
 

@@ -180,6 +180,10 @@ class Problem:
         """Test / bench hook: persistent TMA-fed update kernel (default) or the round-1 cp.async kernel."""
         _check(self.L.rcvd_debug_set_update_kernel(self.h, C.c_int32(1 if tma else 0), C.c_int32(side_items_per_cta)))
 
+    def set_eval_only(self, on=True):
+        """Test / bench hook: the handle only evaluates cost / gradient; no matrix storage is allocated."""
+        _check(self.L.rcvd_debug_set_eval_only(self.h, C.c_int32(1 if on else 0)))
+
     def set_distributed(self, on=True):
         """Test / bench hook (nranks > 1): distributed factorisation (default) or the round-1 replicated scheme."""
         _check(self.L.rcvd_debug_set_distributed(self.h, C.c_int32(1 if on else 0)))
