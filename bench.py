@@ -46,9 +46,15 @@ WORKLOADS = {
     "config5_300f_384x224_grid16x12_sep10_holes50_dolly": dict(frames=300, w=384, h=224, gx=16, gy=12, sep=10, scene=dict(hole_fraction=0.29, dolly=0.008)),
 }
 METRIC = "flow_residual_constraints_per_sec_per_gn_iteration"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/), config 2;
-# per-launch averages of the captured launches.
-NCU_TRAFFIC = {"gemm_nt": 18.49e6, "accumulate": 149.1e6}   # gemm_nt: mean of the 3 captured launches (grids 288/1200/352 CTAs), profiles/r1_ncu_k_gemm_nt.txt
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the two roofline kernels, from the `ncu --set full` captures of THIS
+    round's kernels (profiles/r2_ncu_traffic.json, written by tools/round_profiles_post.sh together with the kernel names and the capture
+    command); null when the file is missing or was captured for other kernels."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")))
+        return {"update": t["k_update_tma"]["dram_bytes_per_launch"], "accumulate": t["k_accumulate_runs"]["dram_bytes_per_launch"], "source": t["source"]}
+    except Exception:
+        return {"update": None, "accumulate": None, "source": None}
 
 
 def build_case(wl, frames=None, sep=None, seed=2, valid_fraction=1.0):
@@ -313,21 +319,23 @@ def run_ours(args):
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    traffic = ncu_traffic()
     # algorithmic bytes of the residual/Jacobian/accumulate pass: 24 B per constraint + per pair
     # ids + 2 parameter vectors + the outputs (gradient + H blocks of the original structure)
     nf, npad = info["stride"], info["npad"]
     alg_bytes = 24.0 * C_total + len(pairs) * (8 + 16 * nf) + 8.0 * cfg.num_frames * nf + 8.0 * info["h_blocks"] * nf * nf
-    roof_acc = {"bound": "hbm", "kernel": "gn_accumulate (k_accumulate_fast + k_regularisers)", "achieved": alg_bytes / (acc_ms * 1e-3) / 1e9,
+    roof_acc = {"bound": "hbm", "kernel": "gn_accumulate (memset of H + k_accumulate_runs + k_regularisers + cost reduction)", "achieved": alg_bytes / (acc_ms * 1e-3) / 1e9,
                 "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / (acc_ms * 1e-3) / 1e9 / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650 GB/s",
-                "traffic": NCU_TRAFFIC.get("accumulate"), "ms": acc_ms,
-                "note": "fp64 Jacobian arithmetic bound, not HBM bound: see DESIGN.md section 5"}
-    # dominant kernel of the step: k_gemm_nt, the fp64 tensor-core block updates of the sparse Cholesky
+                "traffic": traffic["accumulate"], "traffic_source": traffic["source"], "ms": acc_ms,
+                "note": "latency / fp64-issue bound at matchSeparation 10 (22 MB of records, L2 resident), not HBM bound: see DESIGN.md section 4"}
+    traffic_note = None
+    # dominant kernel of the step: k_update_tma, the fp64 tensor-core block updates of the sparse Cholesky
     n_g = max(lin_prof["gemm_launches"], 1.0)
     g_tf = lin_prof["gemm_flops"] / max(lin_prof["gemm_ms"] * 1e-3, 1e-12) / 1e12
-    roof = {"bound": "tensor", "kernel": "k_gemm_nt (fp64 DMMA Schur updates of the block Cholesky)", "achieved": g_tf, "peak": peak64, "unit": "TFLOP/s",
+    roof = {"bound": "tensor", "kernel": "k_update_tma (TMA-fed fp64 DMMA Schur updates of the block Cholesky)" if not args.legacy_update else "k_gemm_nt (round-1 cp.async kernel)", "achieved": g_tf, "peak": peak64, "unit": "TFLOP/s",
             "frac": g_tf / peak64, "peak_source": "fp64 DMMA.8x8x4 register loop measured live (rcvd_debug_fp64_tensor_peak); MEASURED_PEAKS.json has no fp64 figure",
-            "traffic": NCU_TRAFFIC.get("gemm_nt"), "launches_per_step": int(n_g), "avg_launch_us": lin_prof["gemm_ms"] * 1e3 / n_g,
+            "traffic": traffic["update"], "traffic_source": traffic["source"], "launches_per_step": int(n_g), "avg_launch_us": lin_prof["gemm_ms"] * 1e3 / n_g,
             "flops_per_launch": lin_prof["gemm_flops"] / n_g, "share_of_step_serialised": lin_prof["gemm_ms"] / max(sum(lin_prof[k] for k in ("load_ms", "potrf_ms", "trinv_ms", "trsm_ms", "gemm_ms", "solve_ms")) + acc_ms, 1e-9)}
     line = {"metric": METRIC, "value": C_total / (ms * 1e-3), "unit": "constraints/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

@@ -58,9 +58,3 @@ def setup_problem(P, cfg, pairs, offs, rec, med, x, adaptive=None):
     P.set_constraints(pairs, offs, rec)
     P.set_state(x)
     return P
-
-
-def gauge_align(x, ref, nf_pose=7):
-    """Similarity-align camera positions of x to ref (Umeyama without scale: the scale is fixed by the
-    scale regulariser) and return aligned relative poses for gauge-invariant comparison."""
-    return x
