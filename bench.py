@@ -356,10 +356,14 @@ def run_ours(args):
             line["cpu_baseline"] = {"error": str(e)}
     if world == 1 and not args.skip_pose_opt:
         # metric (ii): pose-optimisation wall-clock through the reference-facing module (lib_python) on a 300-frame directory on disk
+        # (own process: a fresh CUDA context and allocator, as a pose_optimization.py run has -- inside this process the same call
+        # measured 2-3x slower after the bench's other work)
         try:
-            sys.path.insert(0, os.path.join(ROOT, "tools"))
-            import bench_pose_opt
-            line["pose_opt_wallclock"] = bench_pose_opt.run(frames=args.pose_opt_frames, max_iterations=args.pose_opt_iterations, autodiff_iterations=1, skip_cpu=args.skip_cpu)
+            cmd = [sys.executable, os.path.join(ROOT, "tools", "bench_pose_opt.py"), "--frames", str(args.pose_opt_frames), "--max-iterations", str(args.pose_opt_iterations), "--autodiff-iterations", "1"]
+            if args.skip_cpu:
+                cmd.append("--skip-cpu")
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+            line["pose_opt_wallclock"] = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1]) if out.returncode == 0 else {"error": out.stderr[-600:]}
         except Exception as e:
             line["pose_opt_wallclock"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)

@@ -320,6 +320,9 @@ class DepthVideoPoseOptimizer {
     int pairCount = 0; int64_t constraintCount = 0;
   };
   ProblemArrays buildProblem(const Params& params, const FlowConstraintsCollection* constraints, double depthDeformReg, bool normalize);
+  // record cache of one poseOptimization() call (see buildProblem)
+  bool recordCacheOn_ = false, recordCacheValid_ = false; std::vector<int32_t> cachedPairFrames_; std::vector<int64_t> cachedOffsets_; std::vector<float> cachedRecords_;
+  int cachedPairCount_ = 0; int64_t cachedConstraintCount_ = 0;
   const std::vector<std::array<double, 7>>& poseParams() const { return poseParams_; }
  private:
   void solveAndWriteBack(ProblemArrays& pa, const Params& params, bool writePoses);

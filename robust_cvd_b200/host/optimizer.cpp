@@ -92,7 +92,10 @@ DepthVideoPoseOptimizer::ProblemArrays DepthVideoPoseOptimizer::buildProblem(con
   }
   // static-scene constraints (addStaticSceneLoss :1149-1240, Observation :104-117)
   pa.offsets.assign(1, 0);
-  if (!normalize && constraints) {
+  if (!normalize && constraints && recordCacheOn_ && recordCacheValid_) {
+    // the coarse-to-fine steps of one poseOptimization() call see the same constraints and source depths: the records are assembled once
+    pa.pairFrames = cachedPairFrames_; pa.offsets = cachedOffsets_; pa.records = cachedRecords_; pa.pairCount = cachedPairCount_; pa.constraintCount = cachedConstraintCount_;
+  } else if (!normalize && constraints) {
     const float invAspect = video_->invAspect();
     for (const auto& kv : constraints->pairs()) {
       const int f0 = kv.first.first, f1 = kv.first.second;
@@ -124,6 +127,7 @@ DepthVideoPoseOptimizer::ProblemArrays DepthVideoPoseOptimizer::buildProblem(con
       pa.offsets.push_back(pa.offsets.back() + n);
       pa.constraintCount += n;
     }
+    if (recordCacheOn_) { cachedPairFrames_ = pa.pairFrames; cachedOffsets_ = pa.offsets; cachedRecords_ = pa.records; cachedPairCount_ = pa.pairCount; cachedConstraintCount_ = pa.constraintCount; recordCacheValid_ = true; }
   }
   // scene-flow smoothness constraints (addSceneFlowSmoothnessLoss :1242-1339): only if either weight is positive (:899-901)
   pa.tripOffsets.assign(1, 0);
@@ -243,6 +247,11 @@ void DepthVideoPoseOptimizer::poseOptimization(const Params& params, const FlowC
   DepthStream& ds = video_->depthStream(depthStream_);
   const std::array<int, 3> initGrid = gridSize(ds.depthXformDesc());
   DepthVideoProcessor processor(video_);
+  struct CacheScope {   // observation records (constraint locations + source depths) do not change between the steps of this call
+    DepthVideoPoseOptimizer* o;
+    explicit CacheScope(DepthVideoPoseOptimizer* o_) : o(o_) { o->recordCacheOn_ = true; o->recordCacheValid_ = false; }
+    ~CacheScope() { o->recordCacheOn_ = false; o->recordCacheValid_ = false; std::vector<float>().swap(o->cachedRecords_); }
+  } cacheScope(this);
   if (params.deferredSpatialOpt) {
     DepthVideoProcessor::Params pp; pp.depthStream = depthStream_; pp.spatialXformDesc.type = XformType::Spatial; pp.spatialXformDesc.depthType = DepthXformType::None; pp.spatialXformDesc.spatialType = SpatialXformType::Identity;
     processor.resetSpatialXforms(pp);
