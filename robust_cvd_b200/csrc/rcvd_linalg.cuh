@@ -163,11 +163,100 @@ __device__ __forceinline__ void warp_chol16(double* __restrict__ D, double* __re
 }
 
 #ifdef RCVD_POTRF_PHASES   // tools/potrf_phases.cu: cycle counts per phase of CTA 0 (thread 0's view)
-__device__ long long g_potrf_phase[8];
+__device__ long long g_potrf_phase[16];
 #define POTRF_PHASE(n) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long now_ = clock64(); g_potrf_phase[n] += now_ - last_; last_ = now_; } } while (0)
+#define CHOL_PHASE(n) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long now_ = clock64(); g_potrf_phase[n] += now_ - cl_; cl_ = now_; } } while (0)
 #else
+#define CHOL_PHASE(n) do { } while (0)
 #define POTRF_PHASE(n) do { } while (0)
 #endif
+
+// Round 2: 4x4-blocked Cholesky of one 16x16 tile by a single warp.  The pivot chain of warp_chol16 is 16 x (shuffle, rsqrt, mul,
+// 15 shuffle+FMA column updates) ~ 5.6 k cycles, most of it the shuffle traffic of the rank-1 updates.  Here the tile lives in the
+// DMMA accumulator fragments (three 8x8 units of the lower triangle); per block of four columns every lane factors the 4x4 diagonal block
+// redundantly from ten broadcast shared-memory loads (no communication inside the four-pivot chain), the lanes of the rows below solve
+// their 4-wide panel row, and the rank-4 trailing update is three DMMA.8x8x4 with K = 4.  Same outputs as warp_chol16: L in the
+// swizzled tile (lower triangle), reciprocal pivots in pinv.
+__device__ __forceinline__ void warp_chol16_blocked(double* __restrict__ D, double* __restrict__ pinv, int lane, int* __restrict__ fail) {
+  const int g = lane >> 2, t = lane & 3;
+  double c[3][2];                                  // units (0,0), (1,0), (1,1): rows 8*ui + g, columns 8*uj + 2t, + 1
+  const int ui[3] = {0, 1, 1}, uj[3] = {0, 0, 1};
+#pragma unroll
+  for (int u = 0; u < 3; ++u) { const double2 v = *reinterpret_cast<const double2*>(&D[swz(8 * ui[u] + g, 8 * uj[u] + 2 * t)]); c[u][0] = v.x; c[u][1] = v.y; }
+  bool bad = false;
+#ifdef RCVD_POTRF_PHASES
+  long long cl_ = clock64();
+#endif
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int k0 = 4 * b;
+    if (b > 0) {
+      // the trailing part of the fragments (columns >= k0) goes back to shared memory; columns < k0 there already hold L
+#pragma unroll
+      for (int u = 0; u < 3; ++u) if (8 * uj[u] + 2 * t >= k0) *reinterpret_cast<double2*>(&D[swz(8 * ui[u] + g, 8 * uj[u] + 2 * t)]) = make_double2(c[u][0], c[u][1]);
+    }
+    __syncwarp();
+    // 1. the 4x4 diagonal block, on every lane (broadcast loads)
+    double a00 = D[swz(k0, k0)], a10 = D[swz(k0 + 1, k0)], a11 = D[swz(k0 + 1, k0 + 1)], a20 = D[swz(k0 + 2, k0)], a21 = D[swz(k0 + 2, k0 + 1)],
+           a22 = D[swz(k0 + 2, k0 + 2)], a30 = D[swz(k0 + 3, k0)], a31 = D[swz(k0 + 3, k0 + 1)], a32 = D[swz(k0 + 3, k0 + 2)], a33 = D[swz(k0 + 3, k0 + 3)];
+    CHOL_PHASE(8);
+    // Pivots in PAIRS: for the 2x2 leading block [[a, b], [b, c]] the second reciprocal pivot is 1/sqrt(c - b^2/a) = rsqrt(a c - b^2) sqrt(a),
+    // so rsqrt(a) and rsqrt(a c - b^2) issue side by side (the determinant carries the same cancellation error, relative to the pivot,
+    // as c - (b/sqrt a)^2 does) -- two rsqrt latencies per 4x4 block on the dependent chain instead of four.
+    double t01 = a10 * a10;
+    double det01 = fma(a00, a11, -t01);
+    if (!(a00 > 0.0) || !isfinite(a00)) { bad = true; a00 = 1.0; det01 = 1.0; }
+    if (!(det01 > 0.0) || !isfinite(det01)) { bad = true; det01 = a00; }
+    const double p0 = rsqrt(a00), r01 = rsqrt(det01);
+    const double sq0 = a00 * p0;                    // sqrt(a00) = L[0][0]
+    const double p1 = r01 * sq0;
+    const double l11 = det01 * r01 * p0;            // sqrt(det01 / a00) = L[1][1]
+    const double l10 = a10 * p0, l20 = a20 * p0, l30 = a30 * p0;
+    const double l21 = (a21 - l20 * l10) * p1, l31 = (a31 - l30 * l10) * p1;
+    double b22 = fma(-l21, l21, fma(-l20, l20, a22)), b33 = fma(-l31, l31, fma(-l30, l30, a33));
+    const double b32 = fma(-l31, l21, fma(-l30, l20, a32));
+    double det23 = fma(b22, b33, -(b32 * b32));
+    if (!(b22 > 0.0) || !isfinite(b22)) { bad = true; b22 = 1.0; det23 = 1.0; }
+    if (!(det23 > 0.0) || !isfinite(det23)) { bad = true; det23 = b22; }
+    const double p2 = rsqrt(b22), r23 = rsqrt(det23);
+    const double sq2 = b22 * p2;
+    const double p3 = r23 * sq2;
+    const double l33 = det23 * r23 * p2;
+    const double l32 = b32 * p2;
+    CHOL_PHASE(9);
+    // 2. block column k0 .. k0+3 of L: lane r (< 16) owns row r.  Rows below the block are solved here (their values are read by no
+    //    other lane in step 1); the rows of the diagonal block itself are written after the warp barrier below, when every lane has
+    //    read the block.  Branch-free so that the four solves interleave with the pivot chain above.
+    const int r = lane & 15;
+    const bool below = lane < 16 && r >= k0 + 4;
+    double x0 = D[swz(r, k0)] * p0;
+    double x1 = (D[swz(r, k0 + 1)] - x0 * l10) * p1;
+    double x2 = (D[swz(r, k0 + 2)] - x0 * l20 - x1 * l21) * p2;
+    double x3 = (D[swz(r, k0 + 3)] - x0 * l30 - x1 * l31 - x2 * l32) * p3;
+    if (below) { D[swz(r, k0)] = x0; D[swz(r, k0 + 1)] = x1; D[swz(r, k0 + 2)] = x2; D[swz(r, k0 + 3)] = x3; }
+    __syncwarp();
+    CHOL_PHASE(10);
+    if (lane == 0) {                                // the diagonal block itself (zeros above the diagonal) and the reciprocal pivots:
+      // every lane holds them, one lane stores them (per-row selects on four lanes compiled to a three-way divergent branch)
+      *reinterpret_cast<double2*>(&D[swz(k0, k0)]) = make_double2(sq0, 0.0);         *reinterpret_cast<double2*>(&D[swz(k0, k0 + 2)]) = make_double2(0.0, 0.0);
+      *reinterpret_cast<double2*>(&D[swz(k0 + 1, k0)]) = make_double2(l10, l11);     *reinterpret_cast<double2*>(&D[swz(k0 + 1, k0 + 2)]) = make_double2(0.0, 0.0);
+      *reinterpret_cast<double2*>(&D[swz(k0 + 2, k0)]) = make_double2(l20, l21);          *reinterpret_cast<double2*>(&D[swz(k0 + 2, k0 + 2)]) = make_double2(sq2, 0.0);
+      *reinterpret_cast<double2*>(&D[swz(k0 + 3, k0)]) = make_double2(l30, l31);          *reinterpret_cast<double2*>(&D[swz(k0 + 3, k0 + 2)]) = make_double2(l32, l33);
+      *reinterpret_cast<double2*>(&pinv[k0]) = make_double2(p0, p1);                      *reinterpret_cast<double2*>(&pinv[k0 + 2]) = make_double2(p2, p3);
+    }
+    // 3. rank-4 trailing update of rows / columns >= k0 + 4 on the tensor cores (operands of eliminated rows masked to zero)
+    if (b < 3) {
+      double pa[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) { const int r = 8 * i + g; pa[i] = r >= k0 + 4 ? D[swz(r, k0 + t)] : 0.0; }
+#pragma unroll
+      for (int u = 0; u < 3; ++u) dmma_8x8x4_fwd(c[u][0], c[u][1], -pa[ui[u]], pa[uj[u]]);
+    }
+    CHOL_PHASE(11);
+  }
+  if (bad && lane == 0) *fail = 1;
+}
+
 
 __global__ void __launch_bounds__(kPotrfSmemThreads) k_potrf_smem(double* __restrict__ Lb, double* __restrict__ invT,
                                                                    const int* __restrict__ frames, int npad, int* __restrict__ fail, int chain_warp) {
@@ -195,57 +284,73 @@ __global__ void __launch_bounds__(kPotrfSmemThreads) k_potrf_smem(double* __rest
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   POTRF_PHASE(0);
-  if (warp == 0) warp_chol16(tiles, pinv, lane, fail);
+  if (warp == 0) { if (chain_warp & 2) warp_chol16_blocked(tiles, pinv, lane, fail); else warp_chol16(tiles, pinv, lane, fail); }
   __syncthreads();
   POTRF_PHASE(1);
   for (int jb = 0; jb < nt; ++jb) {
     const double* D = tiles + (size_t)(jb * (jb + 1) / 2 + jb) * kTileSz;
     const double* pv = pinv + jb * 16;
     // ---- panel by forward substitution (one thread per row below the tile); warp nw-1 computes the tile inverse ----
+    // Chain mode (default): warp 0 solves only the rows of tile (jb+1, jb) -- all its lookahead needs -- updates tile (jb+1, jb+1),
+    // ARRIVES on named barrier 2 and factors the tile; the other warps SYNC on barrier 2 before they start their panel rows, so the
+    // chain warp has the shared-memory pipe and the fp64 pipe to itself for its short serial part, and the others' panel + trailing
+    // tiles run beside the next pivot tile's Cholesky.  (tools/potrf_phases.cu, thread 0's view of one step with every warp entering
+    // the panel and the DMMA section together: panel 1.45 k -- 152 broadcast LDS per row thread, LSU-bound -- + barrier 0.2 k + own
+    // tile update 1.4 k cycles, next to 5.3 k of Cholesky.)
     const int rows = (nt - jb - 1) * 16;
-    if (tid < rows) {
-      const int ti = jb + 1 + (tid >> 4), r = tid & 15;
+    const bool chain = (chain_warp & 1) != 0;
+    int prow = -1;                                   // this thread's panel row (index below the pivot tile), -1: none
+    // (keeping the warps that share the chain warp's scheduler idle made the pivot tile faster, 4.3 k -> 3.9 k cycles, and the other
+    // warps' trailing update slower by more: 2.77 against 2.68 ms per factorisation)
+    const int nwork = nw - 1, widx = warp - 1;       // worker warps beside the chain warp
+    if (chain) { if (warp == 0) { if (lane < 16 && rows > 0) prow = lane; } else if (widx * 32 + lane < rows - 16) prow = 16 + widx * 32 + lane; }
+    else if (tid < rows) prow = tid;
+    if (chain && warp != 0) asm volatile("bar.sync 2, %0;" ::"n"(kPotrfSmemThreads) : "memory");
+    if (prow >= 0) {
+      const int ti = jb + 1 + (prow >> 4), r = prow & 15;
       double* Tt = tiles + (size_t)(ti * (ti + 1) / 2 + jb) * kTileSz;
       double a[16];
 #pragma unroll
-      for (int q = 0; q < 16; ++q) a[q] = Tt[swz(r, q)];
+      for (int q = 0; q < 16; q += 2) { const double2 v = *reinterpret_cast<const double2*>(&Tt[swz(r, q)]); a[q] = v.x; a[q + 1] = v.y; }
+      // right-looking substitution: once x_q is final every later column takes its term at once (independent FMAs) -- the dependent
+      // chain is one multiply + one FMA per column instead of the 120 chained FMAs of the dot-product form.  Two columns per pass so
+      // that L comes in as 16-byte pairs (64 + 16 shared-memory loads per row instead of 120 + 32: the panel is LSU-bound).
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        double sacc = a[c];
+      for (int q = 0; q < 16; q += 2) {
+        const double2 pq = *reinterpret_cast<const double2*>(&pv[q]);
+        const double2 dq = *reinterpret_cast<const double2*>(&D[swz(q + 1, q)]);     // L[q+1][q], (L[q+1][q+1] unused)
+        a[q] *= pq.x;
+        a[q + 1] = (a[q + 1] - a[q] * dq.x) * pq.y;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) if (q < c) sacc -= a[q] * D[swz(c, q)];
-        a[c] = sacc * pv[c];
+        for (int c = 0; c < 16; ++c) if (c > q + 1) { const double2 l = *reinterpret_cast<const double2*>(&D[swz(c, q)]); a[c] -= a[q] * l.x; a[c] -= a[q + 1] * l.y; }
       }
 #pragma unroll
-      for (int q = 0; q < 16; ++q) Tt[swz(r, q)] = a[q];
+      for (int q = 0; q < 16; q += 2) *reinterpret_cast<double2*>(&Tt[swz(r, q)]) = make_double2(a[q], a[q + 1]);
     } else if (warp == nw - 1 && lane < 16) {
       // inverse of the triangular tile (only needed by k_trinv): column `lane`, forward substitution
       const int cidx = lane;
       double xcol[16];
 #pragma unroll
-      for (int r = 0; r < 16; ++r) {
-        double s0 = (r == cidx) ? 1.0 : 0.0, s1 = 0.0;
+      for (int r = 0; r < 16; ++r) xcol[r] = (r == cidx) ? 1.0 : 0.0;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) if (q < r) { const double lrq = D[swz(r, q)]; if (q & 1) s1 -= lrq * xcol[q]; else s0 -= lrq * xcol[q]; }
-        xcol[r] = (r < cidx) ? 0.0 : (s0 + s1) * pv[r];
+      for (int q = 0; q < 16; q += 2) {            // right-looking, two columns per pass, like the panel rows
+        const double2 pq = *reinterpret_cast<const double2*>(&pv[q]);
+        const double2 dq = *reinterpret_cast<const double2*>(&D[swz(q + 1, q)]);
+        xcol[q] *= pq.x;
+        xcol[q + 1] = (xcol[q + 1] - xcol[q] * dq.x) * pq.y;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) if (r > q + 1) { const double2 l = *reinterpret_cast<const double2*>(&D[swz(r, q)]); xcol[r] -= l.x * xcol[q]; xcol[r] -= l.y * xcol[q + 1]; }
       }
 #pragma unroll
       for (int r = 0; r < 16; ++r) iT[(size_t)jb * 256 + r * 16 + cidx] = xcol[r];
     }
     POTRF_PHASE(2);
-    __syncthreads();
+    if (!chain) __syncthreads();
+    else if (warp != 0) asm volatile("bar.sync 3, %0;" ::"n"(kPotrfSmemThreads - 32) : "memory");
     POTRF_PHASE(3);
     // ---- trailing update (DMMA) with lookahead: warp 0 updates tile (jb+1, jb+1) first and factors it at once ----
     const int m = nt - jb - 1, ntr = m * (m + 1) / 2;
-    // warp 0 owns the chain: it updates tile (jb+1, jb+1) and factors it at once (lookahead); the other warps share the rest
-    // (measured: 88.7 -> 83.0 us per 208x208 block in tools/potrf_phases.cu)
-    for (int tl = (chain_warp ? (warp == 0 ? 0 : warp) : warp); tl < ((chain_warp && warp == 0) ? min(ntr, 1) : ntr); tl += (chain_warp ? nw - 1 : nw)) {
-      // tile order: tl = 0 is (jb+1, jb+1)
-      int ti = (int)((sqrtf(8.f * tl + 1.f) - 1.f) * 0.5f);
-      while ((ti + 1) * (ti + 2) / 2 <= tl) ++ti;
-      while (ti * (ti + 1) / 2 > tl) --ti;
-      const int tj = tl - ti * (ti + 1) / 2;
-      const int gi = jb + 1 + ti, gj = jb + 1 + tj;
+    auto upd_tile = [&](int gi, int gj) -> double* {
       const double* Xi = tiles + (size_t)(gi * (gi + 1) / 2 + jb) * kTileSz;
       const double* Xj = tiles + (size_t)(gj * (gj + 1) / 2 + jb) * kTileSz;
       double* Ct = tiles + (size_t)(gi * (gi + 1) / 2 + gj) * kTileSz;
@@ -258,7 +363,34 @@ __global__ void __launch_bounds__(kPotrfSmemThreads) k_potrf_smem(double* __rest
           double2* ptr = reinterpret_cast<double2*>(&Ct[swz(i * 8 + g, j * 8 + 2 * t)]);
           double2 v = *ptr; v.x -= acc[i][j][0]; v.y -= acc[i][j][1]; *ptr = v;
         }
-      if (tl == 0) { __syncwarp(); POTRF_PHASE(4); warp_chol16(Ct, pinv + (jb + 1) * 16, lane, fail); POTRF_PHASE(5); }   // lookahead: next diagonal tile
+      return Ct;
+    };
+    auto tile_of = [&](int tl, int& gi, int& gj) {   // tile order: tl = 0 is (jb+1, jb+1)
+      int ti = (int)((sqrtf(8.f * tl + 1.f) - 1.f) * 0.5f);
+      while ((ti + 1) * (ti + 2) / 2 <= tl) ++ti;
+      while (ti * (ti + 1) / 2 > tl) --ti;
+      gi = jb + 1 + ti; gj = jb + 1 + (tl - ti * (ti + 1) / 2);
+    };
+    if (chain) {
+      // warp 0 owns the chain (measured: 88.7 -> 83.0 us per 208x208 block in tools/potrf_phases.cu): its panel rows, tile (jb+1, jb+1)
+      // and the next pivot tile, with the SM to itself until it arrives on barrier 2
+      if (warp == 0) {
+        double* Ct = nullptr;
+        if (ntr > 0) { __syncwarp(); Ct = upd_tile(jb + 1, jb + 1); }
+        __threadfence_block();
+        asm volatile("bar.arrive 2, %0;" ::"n"(kPotrfSmemThreads) : "memory");
+        POTRF_PHASE(4);
+        if (ntr > 0) { __syncwarp(); if (chain_warp & 2) warp_chol16_blocked(Ct, pinv + (jb + 1) * 16, lane, fail); else warp_chol16(Ct, pinv + (jb + 1) * 16, lane, fail); }
+        POTRF_PHASE(5);
+      } else {
+        for (int tl = 1 + widx; tl < ntr; tl += nwork) { int gi, gj; tile_of(tl, gi, gj); upd_tile(gi, gj); }
+      }
+    } else {
+      for (int tl = warp; tl < ntr; tl += nw) {
+        int gi, gj; tile_of(tl, gi, gj);
+        double* Ct = upd_tile(gi, gj);
+        if (tl == 0) { __syncwarp(); if (chain_warp & 2) warp_chol16_blocked(Ct, pinv + (jb + 1) * 16, lane, fail); else warp_chol16(Ct, pinv + (jb + 1) * 16, lane, fail); }
+      }
     }
     POTRF_PHASE(6);
     __syncthreads();
@@ -530,16 +662,18 @@ __global__ void __launch_bounds__(128) k_trsm_ll(double* __restrict__ T, const d
   const int nt = npad / 16;
   const int rows = min(kTrsmStrip, npad - m0);
   // load the A strip (rows beyond the block are zero-filled)
-  for (int e = tid; e < kTrsmStrip * (npad / 2); e += 128) {
-    const int r = e / (npad / 2), c = (e % (npad / 2)) * 2;
+  // (eight threads per row, 128 contiguous bytes; no index division -- npad is a run-time value and the divisions of the flat-index
+  // form showed up at the top of the stall samples of this latency-bound kernel)
+  for (int r = tid >> 3; r < kTrsmStrip; r += 16) {
     const bool v = r < rows;
-    cp_async16(&Xs[(size_t)r * ld + c], A + (size_t)(v ? m0 + r : 0) * npad + c, v);
+    const double* src = A + (size_t)(v ? m0 + r : 0) * npad;
+    for (int c = (tid & 7) * 2; c < npad; c += 16) cp_async16(&Xs[(size_t)r * ld + c], src + c, v);
   }
   auto stage = [&](int jt) {   // L row panel (columns [0, jt*16)) and Di of step jt into ring slot jt % kTrsmAhead; always one commit group (may be empty)
     if (jt < nt) {
       double* ls = Ls + (size_t)(jt % kTrsmAhead) * 16 * ld; double* dsm = Ds + (jt % kTrsmAhead) * 320;
       const int kw = jt * 16;
-      for (int e = tid; e < 16 * (kw / 2); e += 128) { const int r = e / (kw / 2), c = (e % (kw / 2)) * 2; cp_async16(&ls[(size_t)r * ld + c], Lk + (size_t)(jt * 16 + r) * npad + c, true); }
+      { const int r = tid >> 3; const double* src = Lk + (size_t)(jt * 16 + r) * npad; for (int c = (tid & 7) * 2; c < kw; c += 16) cp_async16(&ls[(size_t)r * ld + c], src + c, true); }
       { const int r = tid >> 3, c = (tid & 7) * 2; cp_async16(&dsm[r * 20 + c], iT + (size_t)jt * 256 + r * 16 + c, true); }
     }
     cp_async_commit();
@@ -555,16 +689,39 @@ __global__ void __launch_bounds__(128) k_trsm_ll(double* __restrict__ T, const d
     double acc[NI][2][2];
 #pragma unroll
     for (int i = 0; i < NI; ++i) { acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0; }
-    for (int k4 = 0; k4 < jt * 4; ++k4) {
-      double af[NI], bf[2];
+    // K loop over the jt finished column tiles, 16 columns (four DMMA k-steps) at a time; the fragments of tile kt + 1 are loaded
+    // before the eight DMMAs of tile kt issue (a one-k-step loop exposed the shared-memory latency on every step: this kernel is a
+    // 13-step latency chain on the narrow levels)
+    {
+      double af[2][4][NI], bf[2][4][2];
+      auto frag = [&](int kt, int buf) {
 #pragma unroll
-      for (int i = 0; i < NI; ++i) af[i] = Xs[(size_t)(wr + i * 8 + g) * ld + k4 * 4 + t];
+        for (int q = 0; q < 4; ++q) {
 #pragma unroll
-      for (int j = 0; j < 2; ++j) bf[j] = ls[(size_t)(j * 8 + g) * ld + k4 * 4 + t];
+          for (int i = 0; i < NI; ++i) af[buf][q][i] = Xs[(size_t)(wr + i * 8 + g) * ld + kt * 16 + q * 4 + t];
 #pragma unroll
-      for (int i = 0; i < NI; ++i)
+          for (int j = 0; j < 2; ++j) bf[buf][q][j] = ls[(size_t)(j * 8 + g) * ld + kt * 16 + q * 4 + t];
+        }
+      };
+      if (jt > 0) frag(0, 0);
+      for (int kt = 0; kt < jt; kt += 2) {
+        if (kt + 1 < jt) frag(kt + 1, 1);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int i = 0; i < NI; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[0][q][i], bf[0][q][j]);
+        if (kt + 1 < jt) {
+          if (kt + 2 < jt) frag(kt + 2, 0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int i = 0; i < NI; ++i)
+#pragma unroll
+              for (int j = 0; j < 2; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[1][q][i], bf[1][q][j]);
+        }
+      }
     }
     // Tt = A[:, jt] - acc, written back in place (each lane owns its C-fragment positions), then X[:, jt] = Tt * Di^T
 #pragma unroll
@@ -748,6 +905,127 @@ __global__ void __launch_bounds__(256) k_bwd_diag(const double* __restrict__ inv
     x[(size_t)frame * npad + j] = s;
   }
 }
+
+// ---------------------------------------------------------------------------
+// Round 2: the whole forward + backward substitution as ONE persistent dataflow kernel.  The level-scheduled version above is
+// 4 launches per level (172 at config 2), each a single short wave: 1.35 ms of launch latency for ~0.3 ms of memory traffic.  Here the
+// same GEMVs are tasks of a list in topological order (level-major; forward levels ascending, then backward levels descending), cut
+// into kSubChunk-row (forward) / -column (backward) chunks.  A CTA takes the next task with an atomic ticket, waits on the counters its
+// inputs signal, computes, signals.  Dependencies always point to EARLIER tasks of the list, which running CTAs have taken, so the
+// wait loops cannot deadlock whatever the number of resident CTAs is; and the waits are per frame, not per level.
+//   FDIAG(k):   y_k      = inv(L_kk) rhs_k            waits until every FUPD(k, .) chunk has landed     signals fdone[k]
+//   FUPD(r,k):  rhs_r   -= T_rk y_k                    waits for fdone[k] == chunks                      signals fin[r]
+//   BUPD(r,k):  y_k     -= T_rk^T x_r                  waits for bdone[r] == chunks                      signals bin[k]
+//   BDIAG(k):   x_k      = inv(L_kk)^T y_k             waits for fdone[k] and every BUPD(., k) chunk     signals bdone[k]
+// Vectors written by other SMs are read with ld.global.cg (L2) after the acquire; matrices are immutable during the kernel.
+// ---------------------------------------------------------------------------
+constexpr int kSubChunk = 64;
+constexpr int kSubThreads = 256;
+struct SubTask { int type; int blk; int r; int k; int chunk; };   // type 0 FDIAG, 1 FUPD, 2 BUPD, 3 BDIAG
+struct SubCounters { int* ticket; int* fin; int* fdone; int* bin; int* bdone; const int* fin_need; const int* bin_need; };
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void sub_wait(const int* c, int need) { while (ld_acquire_gpu(c) < need) __nanosleep(20); }
+
+__device__ __forceinline__ void red_release_add(int* p, int v) { asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ double2 ldcg2(const double* p) { return __ldcg(reinterpret_cast<const double2*>(p)); }
+
+__global__ void __launch_bounds__(kSubThreads) k_substitution(const double* __restrict__ invL, const double* __restrict__ T, double* rhs, double* y, double* x,
+                                                              const SubTask* __restrict__ tasks, int ntasks, SubCounters cn, int npad) {
+  extern __shared__ __align__(16) double red[];   // [8][kSubChunk + 2] column partials
+  __shared__ int s_task;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nchunks = (npad + kSubChunk - 1) / kSubChunk;
+  const size_t bs = (size_t)npad * npad;
+  for (;;) {
+    if (tid == 0) s_task = atomicAdd(cn.ticket, 1);
+    __syncthreads();
+    const int ti = s_task;
+    if (ti >= ntasks) break;
+    const SubTask tk = tasks[ti];
+    const int c0 = tk.chunk * kSubChunk, c1 = min(npad, c0 + kSubChunk);
+    // input vector (written by other SMs: read through L2 after the acquire) and the immutable matrix block of the task
+    const double* vin = tk.type == 0 ? rhs + (size_t)tk.k * npad : (tk.type == 2 ? x + (size_t)tk.r * npad : y + (size_t)tk.k * npad);
+    const double* M = (tk.type == 0 || tk.type == 3) ? invL + (size_t)tk.k * bs : T + (size_t)tk.blk * bs;
+    auto dep_wait = [&]() {
+      if (tid == 0) {
+        if (tk.type == 0) sub_wait(cn.fin + tk.k, cn.fin_need[tk.k]);
+        else if (tk.type == 1) sub_wait(cn.fdone + tk.k, nchunks);
+        else if (tk.type == 2) sub_wait(cn.bdone + tk.r, nchunks);
+        else { sub_wait(cn.fdone + tk.k, nchunks); sub_wait(cn.bin + tk.k, cn.bin_need[tk.k]); }
+      }
+      __syncthreads();
+    };
+    // A task is one short latency-bound GEMV on the dependency chain.  Every load of a thread is issued before the first is used (a
+    // row-at-a-time loop serialised eight memory latencies per warp), and the matrix part -- up to 256 columns / rows, all of it at
+    // npad <= 256 -- is in flight BEFORE the wait: CTAs take tasks ahead of their inputs, so the matrix latency hides behind the wait.
+    if (tk.type <= 1) {
+      // rows c0 .. c1 of M times the vector: eight rows per warp, 16-byte loads
+      constexpr int RW = kSubChunk / (kSubThreads / 32);
+      const int r0 = c0 + warp * RW;
+      double acc[RW];
+#pragma unroll
+      for (int i = 0; i < RW; ++i) acc[i] = 0.0;
+      for (int qb = 0; qb < npad; qb += 256) {        // 4 x 64 columns per pass: 32 independent 16-byte loads per lane
+        double2 m[4][RW];
+#pragma unroll
+        for (int qi = 0; qi < 4; ++qi) {
+          const int q = qb + qi * 64 + 2 * lane;
+#pragma unroll
+          for (int i = 0; i < RW; ++i) {
+            const int row = r0 + i;
+            const int len = tk.type == 0 ? row + 1 : npad;     // inv(L) is lower triangular
+            m[qi][i] = (row < c1 && q < len) ? *reinterpret_cast<const double2*>(M + (size_t)row * npad + q) : make_double2(0.0, 0.0);
+            if (q + 1 >= len) m[qi][i].y = 0.0;
+          }
+        }
+        if (qb == 0) dep_wait();
+        double2 v[4];
+#pragma unroll
+        for (int qi = 0; qi < 4; ++qi) { const int q = qb + qi * 64 + 2 * lane; v[qi] = q < npad ? ldcg2(vin + q) : make_double2(0.0, 0.0); }
+#pragma unroll
+        for (int qi = 0; qi < 4; ++qi)
+#pragma unroll
+          for (int i = 0; i < RW; ++i) acc[i] += m[qi][i].x * v[qi].x + m[qi][i].y * v[qi].y;
+      }
+#pragma unroll
+      for (int i = 0; i < RW; ++i) {
+        const double sum = warp_sum(acc[i]);
+        const int row = r0 + i;
+        if (lane == 0 && row < c1) { if (tk.type == 0) y[(size_t)tk.k * npad + row] = sum; else red_add(rhs + (size_t)tk.r * npad + row, -sum); }
+      }
+    } else {
+      // columns c0 .. c1 of M^T times the vector: 32 column pairs x 8 row groups, 512 contiguous bytes per row
+      const int cl = tid & 31, rg = tid >> 5, j = c0 + 2 * cl;
+      double ax = 0.0, ay = 0.0;
+      // inv(L)^T: only rows i >= j contribute; the first such row of this row group
+      const int ifirst = tk.type == 3 ? j + ((rg - j) & 7) : rg;
+      for (int ib = ifirst; ib < npad || ib == ifirst; ib += 256) {   // 32 rows of this row group per pass, loads first
+        double2 m[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) { const int i = ib + 8 * u; m[u] = (i < npad && j < c1) ? *reinterpret_cast<const double2*>(M + (size_t)i * npad + j) : make_double2(0.0, 0.0); }
+        if (ib == ifirst) dep_wait();
+        double vi[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) { const int i = ib + 8 * u; vi[u] = i < npad ? __ldcg(vin + i) : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 32; ++u) { const int i = ib + 8 * u; ax += m[u].x * vi[u]; if (tk.type != 3 || i > j) ay += m[u].y * vi[u]; }
+      }
+      red[rg * (kSubChunk + 2) + 2 * cl] = ax; red[rg * (kSubChunk + 2) + 2 * cl + 1] = ay;
+      __syncthreads();
+      if (tid < kSubChunk && c0 + tid < c1) {
+        double sum = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sum += red[q * (kSubChunk + 2) + tid];
+        if (tk.type == 3) x[(size_t)tk.k * npad + c0 + tid] = sum; else red_add(y + (size_t)tk.k * npad + c0 + tid, -sum);
+      }
+    }
+    // the barrier orders every thread's stores / REDs before thread 0's release (cumulativity), like cutlass::Semaphore::release
+    __syncthreads();
+    if (tid == 0) red_release_add(tk.type == 0 ? cn.fdone + tk.k : (tk.type == 1 ? cn.fin + tk.r : (tk.type == 2 ? cn.bin + tk.k : cn.bdone + tk.k)), 1);
+  }
+}
+__host__ __device__ inline size_t substitution_smem_bytes(int) { return (size_t)8 * (kSubChunk + 2) * sizeof(double); }
 
 // ---------------------------------------------------------------------------
 // Factor load: L <- S H S + D2 (lower triangle of diagonal blocks, pad diagonal = 1)

@@ -199,6 +199,9 @@ class Problem:
     def set_trim_gemm(self, on=True):
         _check(self.L.rcvd_debug_set_trim_gemm(self.h, C.c_int32(1 if on else 0)))
 
+    def set_fused_substitution(self, on=True):
+        _check(self.L.rcvd_debug_set_fused_substitution(self.h, C.c_int32(int(on))))
+
     def set_trsm_ll(self, on=True):
         _check(self.L.rcvd_debug_set_trsm_ll(self.h, C.c_int32(1 if on else 0)))
 

@@ -50,8 +50,10 @@ def test_linear_solve(name, overrides):
     res = np.linalg.norm(A @ y - b) / np.linalg.norm(b)
     assert res < 1e-8, res
     assert np.linalg.norm(y - y_ref) / np.linalg.norm(y_ref) < 1e-6
-    # solver variants must agree to round-off: untrimmed update GEMMs, single-stream graph, explicit-inverse TRSM
-    for setter in (lambda: G.set_trim_gemm(False), lambda: G.set_overlap(False), lambda: G.set_trsm_ll(False)):
+    # solver variants must agree to round-off: level-scheduled substitution launches (instead of the persistent dataflow kernel),
+    # round-1 pivot-tile Cholesky, untrimmed update GEMMs, single-stream graph, explicit-inverse TRSM
+    for setter in (lambda: G.set_fused_substitution(False), lambda: G.L.rcvd_debug_set_potrf_chain_warp(G.h, 3), lambda: G.set_trim_gemm(False),
+                   lambda: G.set_overlap(False), lambda: G.set_trsm_ll(False)):
         setter()
         y2 = G.debug_linear_solve(S, D2, b)
         assert np.linalg.norm(y2 - y) / np.linalg.norm(y) < 1e-9
