@@ -321,6 +321,11 @@ void FlowConstraintsCollection::computeTriplet(int triplet) {   // :467-550 (qui
 }
 
 // All pairs and triplets through rcvd_build_constraints, in batches that bound the host staging memory.
+namespace { template <class T> struct RawBuf {   // uninitialised array (new T[n] default-initialises trivial types: no fill)
+  explicit RawBuf(size_t n) : p(n ? new T[n] : nullptr) {}
+  T* data() { return p.get(); }
+  std::unique_ptr<T[]> p;
+}; }
 void FlowConstraintsCollection::computeOnDevice() {
   ColorStream& cs = video_->colorStream("down");
   const int w = cs.width(), h = cs.height();
@@ -340,18 +345,23 @@ void FlowConstraintsCollection::computeOnDevice() {
   std::vector<float> color(size_t(F) * plane * 3), dyn;
   const bool hasDyn = video_->hasColorStream("dynamic_mask");
   int dw = 0, dh = 0;
-  for (auto& kv : local) {
-    const Image* img = cs.frame(kv.first).image();
+  // colour frames (+ distance transforms of the dynamic masks) into the staging arrays: files, PNG decoding and the chamfer pass are
+  // independent per frame -> host threads; the first frame goes alone because it fixes the streams' dimensions
+  std::vector<int> fr; fr.reserve(local.size()); for (auto& kv : local) fr.push_back(kv.first);   // local index = position
+  auto stageFrame = [&](size_t i) {
+    const Image* img = cs.frame(fr[i]).image();
     if (!img) throw std::runtime_error("Missing color frame.");
     if (img->cols != w || img->rows != h || img->type != cvMakeType(CV_32F, 3)) throw std::runtime_error("Color frame has the wrong size or type.");
-    std::memcpy(color.data() + size_t(kv.second) * plane * 3, img->ptr<float>(), plane * 3 * sizeof(float));
+    std::memcpy(color.data() + i * plane * 3, img->ptr<float>(), plane * 3 * sizeof(float));
     if (hasDyn) {
-      Image dd = dynamicDistance(kv.first);
-      if (dyn.empty()) { dw = dd.cols; dh = dd.rows; dyn.resize(size_t(F) * dw * dh); }
+      Image dd = dynamicDistance(fr[i]);
+      if (i == 0) { dw = dd.cols; dh = dd.rows; dyn.resize(size_t(F) * dw * dh); }
       if (dd.cols != dw || dd.rows != dh) throw std::runtime_error("Dynamic masks have inconsistent dimensions.");
-      std::memcpy(dyn.data() + size_t(kv.second) * dw * dh, dd.ptr<float>(), size_t(dw) * dh * sizeof(float));
+      std::memcpy(dyn.data() + i * size_t(dw) * dh, dd.ptr<float>(), size_t(dw) * dh * sizeof(float));
     }
-  }
+  };
+  stageFrame(0);
+  parallelFor(fr.size() - 1, [&](size_t i) { stageFrame(i + 1); });
   rcvd_builder_params prm{};
   prm.num_frames = F; prm.width = w; prm.height = h; prm.dyn_width = dw; prm.dyn_height = dh; prm.match_separation = params_.matchSeparation;
   prm.min_dynamic_distance = params_.minDynamicDistance; prm.inv_aspect = video_->invAspect();
@@ -364,22 +374,48 @@ void FlowConstraintsCollection::computeOnDevice() {
     const size_t budgetLeft = kBatchBytes > np * perPair ? kBatchBytes - np * perPair : 0;
     const size_t nt = pi + np >= keys.size() ? std::min(trips.size() - ti, std::max<size_t>(np == 0 ? 1 : 0, budgetLeft / perTrip)) : 0;
     std::vector<int32_t> pf(np * 2), tf(nt);
-    std::vector<float> pflow(np * plane * 2), tflow(nt * 2 * plane * 2);
-    std::vector<uint8_t> pmask(np * plane), tmask(nt * 2 * plane);
-    for (size_t k = 0; k < np; ++k) {
+    // staging arrays are written slot by slot below: no zero fill (std::vector's value-initialisation of ~0.7 GB per batch cost more
+    // wall-clock than reading and decoding the files)
+    RawBuf<float> pflow(np * plane * 2), tflow(nt * 2 * plane * 2);
+    RawBuf<uint8_t> pmask(np * plane), tmask(nt * 2 * plane);
+    // flow + mask files of the batch (file reads and PNG inflation dominate the builder's wall-clock): one slot per item, host threads
+    parallelFor(np, [&](size_t k) {
       const PairKey& key = keys[pi + k];
       FlowMask fm = loadFlowAndMask(*video_, path_, key.first, key.second);
-      pf[2 * k] = local[key.first]; pf[2 * k + 1] = local[key.second];
+      pf[2 * k] = local.at(key.first); pf[2 * k + 1] = local.at(key.second);
       std::memcpy(pflow.data() + k * plane * 2, fm.flow.ptr<float>(), plane * 2 * sizeof(float)); std::memcpy(pmask.data() + k * plane, fm.mask.ptr<uint8_t>(), plane);
-    }
+    });
     for (size_t k = 0; k < nt; ++k) {
-      const int t = trips[ti + k]; tf[k] = local[t];
-      if (local[t - 1] != local[t] - 1) throw std::runtime_error("Triplet frames must be consecutive in the constraint frame range.");
-      for (int s2 = 0; s2 < 2; ++s2) {
-        FlowMask fm = loadFlowAndMask(*video_, path_, t, s2 == 0 ? t - 1 : t + 1);
-        std::memcpy(tflow.data() + (k * 2 + s2) * plane * 2, fm.flow.ptr<float>(), plane * 2 * sizeof(float)); std::memcpy(tmask.data() + (k * 2 + s2) * plane, fm.mask.ptr<uint8_t>(), plane);
-      }
+      const int t = trips[ti + k]; tf[k] = local.at(t);
+      if (local.at(t - 1) != local.at(t) - 1) throw std::runtime_error("Triplet frames must be consecutive in the constraint frame range.");
     }
+    parallelFor(nt * 2, [&](size_t q) {
+      const size_t k = q / 2; const int s2 = int(q % 2); const int t = trips[ti + k];
+      FlowMask fm = loadFlowAndMask(*video_, path_, t, s2 == 0 ? t - 1 : t + 1);
+      std::memcpy(tflow.data() + (k * 2 + s2) * plane * 2, fm.flow.ptr<float>(), plane * 2 * sizeof(float)); std::memcpy(tmask.data() + (k * 2 + s2) * plane, fm.mask.ptr<uint8_t>(), plane);
+    });
+#ifdef RCVD_STAGE_SELFCHECK   // development check of the threaded staging against a sequential reload (make CXXFLAGS+=-DRCVD_STAGE_SELFCHECK)
+    {
+      for (size_t k = 0; k < np; ++k) {
+        const PairKey& key = keys[pi + k];
+        FlowMask fm = loadFlowAndMask(*video_, path_, key.first, key.second);
+        if (pf[2 * k] != local.at(key.first) || pf[2 * k + 1] != local.at(key.second) || std::memcmp(pflow.data() + k * plane * 2, fm.flow.ptr<float>(), plane * 2 * sizeof(float)) ||
+            std::memcmp(pmask.data() + k * plane, fm.mask.ptr<uint8_t>(), plane)) throw std::logic_error("stage selfcheck: pair staging differs");
+      }
+      for (size_t k = 0; k < nt; ++k) for (int s2 = 0; s2 < 2; ++s2) {
+        const int t = trips[ti + k];
+        FlowMask fm = loadFlowAndMask(*video_, path_, t, s2 == 0 ? t - 1 : t + 1);
+        if (std::memcmp(tflow.data() + (k * 2 + s2) * plane * 2, fm.flow.ptr<float>(), plane * 2 * sizeof(float)) || std::memcmp(tmask.data() + (k * 2 + s2) * plane, fm.mask.ptr<uint8_t>(), plane))
+          throw std::logic_error("stage selfcheck: triplet staging differs");
+      }
+      for (size_t i = 0; i < fr.size(); ++i) {
+        const Image* img = cs.frame(fr[i]).image();
+        if (std::memcmp(color.data() + i * plane * 3, img->ptr<float>(), plane * 3 * sizeof(float))) throw std::logic_error("stage selfcheck: colour staging differs");
+        if (hasDyn) { Image dd = dynamicDistance(fr[i]); if (std::memcmp(dyn.data() + i * size_t(dw) * dh, dd.ptr<float>(), size_t(dw) * dh * sizeof(float))) throw std::logic_error("stage selfcheck: distance staging differs"); }
+      }
+      fprintf(stderr, "stage selfcheck ok: %zu pairs, %zu triplets, %zu frames\n", np, nt, fr.size());
+    }
+#endif
     prm.num_pairs = int(np); prm.num_triplets = int(nt);
     std::vector<int64_t> poff(np + 1, 0), toff(nt + 1, 0);
     const int sep = std::max(1, params_.matchSeparation);

@@ -367,6 +367,12 @@ DepthFrame& DepthStream::frame(int i) { if (i < 0 || i >= int(frames_.size())) t
 void DepthStream::setDir(const std::string& dir) { dir_ = dir; path_ = video_.path() + "/" + dir_; }
 int DepthStream::width() { if (width_ < 0) { for (auto& f : frames_) if (f->sourceDepth()) break; if (width_ < 0) width_ = height_ = 0; } return width_; }
 int DepthStream::height() { width(); return height_; }
+void DepthStream::preloadSourceDepth(const std::vector<int>& frames, bool medians) {
+  if (frames.empty()) return;
+  auto one = [&](size_t i) { DepthFrame& f = frame(frames[i]); if (f.sourceDepth() && medians) f.sourceDepthMedian(); };
+  one(0);
+  parallelFor(frames.size() - 1, [&](size_t i) { one(i + 1); });
+}
 void DepthStream::resetDepthXforms(const XformDescriptor& desc) { depthXformDesc_ = desc; for (auto& f : frames_) f->resetDepthXform(); }
 void DepthStream::resetSpatialXforms(const XformDescriptor& desc) { spatialXformDesc_ = desc; for (auto& f : frames_) f->resetSpatialXform(); }
 

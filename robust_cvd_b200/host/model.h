@@ -8,11 +8,17 @@
 // so small value types and image containers are defined here.
 #pragma once
 #include <array>
+#include <atomic>
+#include <cstdlib>
+#include <exception>
+#include <functional>
+#include <thread>
 #include <cstdint>
 #include <map>
 #include <memory>
 #include <set>
 #include <string>
+#include <system_error>
 #include <utility>
 #include <vector>
 
@@ -22,6 +28,30 @@ namespace rcvdh {
 // CUDA device of every device call of the host layer: the caller's current device (or RCVD_DEVICE); 0 when no device is usable so that
 // the entry point itself reports RCVD_ERR_NO_DEVICE.
 inline int currentDevice() { const int d = rcvd_current_device(); return d < 0 ? 0 : d; }
+// Host-side loops over independent frames / pairs (depth files, medians, observation records): a few threads, results written to
+// per-item slots so that the outcome does not depend on the schedule.  RCVD_HOST_THREADS overrides the count (1 = sequential).
+inline int hostThreads() {
+  if (const char* e = std::getenv("RCVD_HOST_THREADS")) { const int v = std::atoi(e); if (v > 0) return v; }
+  const unsigned hw = std::thread::hardware_concurrency();
+  return int(hw == 0 ? 1 : (hw > 16 ? 16 : hw));
+}
+inline void parallelFor(size_t n, const std::function<void(size_t)>& fn) {
+  const size_t nt = std::min<size_t>(size_t(hostThreads()), n);
+  if (nt <= 1) { for (size_t i = 0; i < n; ++i) fn(i); return; }
+  std::atomic<size_t> next{0}; std::exception_ptr err; std::atomic<bool> failed{false};
+  auto work = [&]() {
+    for (;;) {
+      const size_t i = next.fetch_add(1);
+      if (i >= n || failed.load()) return;
+      try { fn(i); } catch (...) { if (!failed.exchange(true)) err = std::current_exception(); return; }
+    }
+  };
+  std::vector<std::thread> th;
+  for (size_t t = 1; t < nt; ++t) { try { th.emplace_back(work); } catch (const std::system_error&) { break; } }   // no thread to be had: the caller works alone
+  work();
+  for (auto& t : th) t.join();
+  if (err) std::rethrow_exception(err);
+}
 }
 
 namespace rcvdh {
@@ -208,6 +238,9 @@ class DepthStream {
   void resetDepthXforms(const XformDescriptor& desc);
   void resetSpatialXforms(const XformDescriptor& desc);
   void clearCache() { for (auto& f : frames_) f->clearCache(); }
+  // Loads the source depth (and, if asked, the medians) of the given frames on several threads; the first one is loaded alone because it
+  // fixes the stream's dimensions, which the others only compare against.
+  void preloadSourceDepth(const std::vector<int>& frames, bool medians);
   std::string name_, dir_, path_; int width_ = -1, height_ = -1;
   XformDescriptor depthXformDesc_, spatialXformDesc_;
   std::vector<std::unique_ptr<DepthFrame>> frames_;

@@ -71,6 +71,7 @@ DepthVideoPoseOptimizer::ProblemArrays DepthVideoPoseOptimizer::buildProblem(con
   // medians (:1363-1375): over ALL depth samples including zeros, nth_element at size/2
   pa.median.assign(numFrames_, 1.0);
   if (cfg.scale_reg > 0.0) {
+    ds.preloadSourceDepth(std::vector<int>(range.frames.begin(), range.frames.end()), true);   // files + nth_element of every frame, in parallel
     for (int f : range.frames) pa.median[f] = ds.frame(f).sourceDepthMedian();
   }
   // adaptive deformation weights (AdaptiveDeformationCost ctor, :559-619)
@@ -97,19 +98,28 @@ DepthVideoPoseOptimizer::ProblemArrays DepthVideoPoseOptimizer::buildProblem(con
     pa.pairFrames = cachedPairFrames_; pa.offsets = cachedOffsets_; pa.records = cachedRecords_; pa.pairCount = cachedPairCount_; pa.constraintCount = cachedConstraintCount_;
   } else if (!normalize && constraints) {
     const float invAspect = video_->invAspect();
+    // pairs with both ends in range, in map order; their records are assembled in parallel into per-pair slots and concatenated in order
+    struct PairJob { int f0, f1; const std::vector<PairConstraint>* list; const Image* d0; const Image* d1; std::vector<float> rec; };
+    std::vector<PairJob> jobs;
+    { std::set<int> touched;
+      for (const auto& kv : constraints->pairs()) if (range.inRange(kv.first.first) && range.inRange(kv.first.second)) { touched.insert(kv.first.first); touched.insert(kv.first.second); }
+      ds.preloadSourceDepth(std::vector<int>(touched.begin(), touched.end()), false); }
     for (const auto& kv : constraints->pairs()) {
       const int f0 = kv.first.first, f1 = kv.first.second;
       if (!range.inRange(f0) || !range.inRange(f1)) continue;
-      ++pa.pairCount;
       const Image* d0 = ds.frame(f0).sourceDepth(); const Image* d1 = ds.frame(f1).sourceDepth();
       if (!d0 || !d1) throw std::runtime_error("Missing depth image.");
-      const size_t before = pa.records.size();
-      for (const PairConstraint& c : kv.second) {
+      jobs.push_back({f0, f1, &kv.second, d0, d1, {}});
+    }
+    parallelFor(jobs.size(), [&](size_t j) {
+      PairJob& job = jobs[j];
+      job.rec.reserve(job.list->size() * 6);
+      for (const PairConstraint& c : *job.list) {
         if (!c.isStatic) continue;
         float rec[6];
         bool ok = true;
         for (int o = 0; o < 2; ++o) {
-          const Image* d = o ? d1 : d0;
+          const Image* d = o ? job.d1 : job.d0;
           const float lx = c.loc[o][0], ly = c.loc[o][1];
           rec[o * 3] = -1.f + 2.f * lx; rec[o * 3 + 1] = 1.f - 2.f * ly / invAspect;
           int px = int(lx * d->cols), py = int(ly / invAspect * d->rows);
@@ -120,10 +130,16 @@ DepthVideoPoseOptimizer::ProblemArrays DepthVideoPoseOptimizer::buildProblem(con
           if (!std::isfinite(sd) || sd <= 0) ok = false;
         }
         if (!ok) continue;
-        pa.records.insert(pa.records.end(), rec, rec + 6);
+        job.rec.insert(job.rec.end(), rec, rec + 6);
       }
-      const int64_t n = int64_t(pa.records.size() - before) / 6;
-      pa.pairFrames.push_back(f0); pa.pairFrames.push_back(f1);
+    });
+    size_t total = 0; for (const PairJob& job : jobs) total += job.rec.size();
+    pa.records.reserve(total);
+    for (const PairJob& job : jobs) {
+      ++pa.pairCount;
+      pa.records.insert(pa.records.end(), job.rec.begin(), job.rec.end());
+      const int64_t n = int64_t(job.rec.size()) / 6;
+      pa.pairFrames.push_back(job.f0); pa.pairFrames.push_back(job.f1);
       pa.offsets.push_back(pa.offsets.back() + n);
       pa.constraintCount += n;
     }
