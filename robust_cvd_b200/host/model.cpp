@@ -343,7 +343,14 @@ const Image* DepthFrame::sourceDepth() {
   return (source_ && !source_->empty()) ? source_.get() : nullptr;
 }
 const Image* DepthFrame::depth() {
-  if (!xformed_) { const Image* s = sourceDepth(); if (!s) return nullptr; xformed_ = std::make_unique<Image>(depthXform_->apply(*s)); }
+  // lib/DepthStream.cpp:275-291: the transformed depth is re-applied whenever the transform's descriptor or parameters differ from the
+  // ones it was computed with (Python mutates transforms in place, e.g. depthXform().copyFrom(...), after depth() has been called)
+  const Image* s = sourceDepth();
+  if (!s) return nullptr;
+  if (!xformed_ || depthXform_->desc() != appliedDesc_ || depthXform_->params() != appliedParams_) {
+    appliedDesc_ = depthXform_->desc(); appliedParams_ = depthXform_->params();
+    xformed_ = std::make_unique<Image>(depthXform_->apply(*s));
+  }
   return xformed_.get();
 }
 void DepthFrame::setDepth(const Image& depth) {

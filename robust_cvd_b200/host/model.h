@@ -221,6 +221,7 @@ class DepthFrame {
  private:
   DepthVideo& video_; DepthStream& stream_; int index_;
   std::unique_ptr<Image> source_, xformed_; bool sourceLoaded_ = false; bool medianValid_ = false; float median_ = 0.f;
+  XformDescriptor appliedDesc_; std::vector<double> appliedParams_;   // what xformed_ was computed with
   std::unique_ptr<Xform> depthXform_, spatialXform_;
 };
 class DepthStream {
