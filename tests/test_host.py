@@ -240,6 +240,39 @@ def test_problem_assembly_records(scene_dir):
     assert d2["in_range"].tolist() == [1, 1, 1, 1, 0, 0, 0, 0]
 
 
+def test_threaded_assembly_equals_sequential(scene_dir, monkeypatch):
+    """Depth files / medians / observation records are assembled on host threads into per-item slots (model.h parallelFor): the arrays
+    must not depend on the thread count, and a failure inside a worker (missing depth file) must surface as the same RuntimeError."""
+    sc, root, pairs, masks = scene_dir
+
+    def build(threads):
+        monkeypatch.setenv("RCVD_HOST_THREADS", str(threads))
+        v = _open(root)
+        fp = lp.FlowConstraintsParams(); fp.frameRange.resolve(v.numFrames(), True)
+        fc = lp.FlowConstraintsCollection(v, fp); fc.setStaticFlagFromDynamicMask(8)
+        opt = lp.DepthVideoPoseOptimizer(v, v.numDepthStreams() - 1)
+        params = lp.DepthVideoPoseOptimizer.Params(); params.frameRange.fromString("0-7")
+        return opt._buildProblem(params, fc, 0.0, True), opt._buildProblem(params, fc, 0.1, False)
+    (n1, s1), (n4, s4) = build(1), build(4)
+    for a, b in ((n1, n4), (s1, s4)):
+        for k in a:
+            np.testing.assert_array_equal(np.asarray(a[k]), np.asarray(b[k]), err_msg=k)
+    assert s4["records"].size > 0 and np.all(n4["median"] > 0)
+    # a worker's exception is rethrown on the calling thread
+    import shutil, tempfile
+    broken = tempfile.mkdtemp(prefix="rcvd_broken_"); shutil.rmtree(broken); shutil.copytree(root, broken)
+    try:
+        os.remove(f"{broken}/depth_midas2/depth/frame_000005.raw")
+        monkeypatch.setenv("RCVD_HOST_THREADS", "4")
+        v = _open(broken)
+        opt = lp.DepthVideoPoseOptimizer(v, v.numDepthStreams() - 1)
+        params = lp.DepthVideoPoseOptimizer.Params(); params.frameRange.fromString("0-7")
+        with pytest.raises(RuntimeError, match="Missing depth image"):
+            opt._buildProblem(params, None, 0.0, True)
+    finally:
+        shutil.rmtree(broken, ignore_errors=True)
+
+
 def test_adaptive_deformation_node_weights_follow_reference_splat(scene_dir):
     """AdaptiveDeformationCost constructor (reference lib/PoseOptimizer.cpp:559-619): every dynamic-mask pixel is splatted bilinearly onto
     the depth grid into a static or a dynamic accumulator; node weight = dynamic / (dynamic + static).  Restated here in numpy."""
