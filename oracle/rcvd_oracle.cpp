@@ -890,8 +890,14 @@ static double evaluate(Problem& P, bool wantG, bool wantH, double* costStatic = 
     locks.resize(std::max(id, 1)); for (auto& l : locks) omp_init_lock(&l);
   }
   std::vector<omp_lock_t> glocks(wantG ? P.N : 0); for (auto& l : glocks) omp_init_lock(&l);
+  // pairs are visited in a strided order: neighbours in the list share their source frame, and the threads of a dynamic schedule would
+  // queue on that frame's diagonal-block lock (config 2 on 8 vCPU: 1.05 s -> 0.31 s per evaluation with H)
+  int stride = 1; { const int cand[] = {997, 499, 251, 127, 61, 31, 13, 7, 3}; for (int q : cand) if (q < np && np % q != 0) { stride = q; break; } }
+  auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
+  if (np > 0 && gcd(stride, np) != 1) stride = 1;
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : cost)
-  for (int p = 0; p < np; ++p) {
+  for (int q = 0; q < np; ++q) {
+    const int p = int((int64_t(q) * stride) % np);
     const int f0 = P.pairFrames[2 * p], f1 = P.pairFrames[2 * p + 1];
     const int64_t beg = P.offsets[p], end = P.offsets[p + 1];
     if (beg == end) continue;
